@@ -1,0 +1,83 @@
+// common.cuh — error handling, stream-ordered scratch memory and small device helpers shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "field.cuh"
+
+namespace zk {
+
+// ---- status codes of the C ABI (include/zkdl_b200.h)
+enum : int { ZK_OK = 0, ZK_ERR_DIM = 1, ZK_ERR_CUDA = 2, ZK_ERR_ARG = 3, ZK_ERR_NCCL = 4 };
+
+void set_last_error(const char* fmt, ...);
+
+#define ZK_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      zk::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));       \
+      return zk::ZK_ERR_CUDA;                                                                          \
+    }                                                                                                  \
+  } while (0)
+#define ZK_CHECK_LAUNCH() ZK_CUDA(cudaGetLastError())
+#define ZK_REQUIRE(cond, code, msg)                                                                    \
+  do {                                                                                                 \
+    if (!(cond)) { zk::set_last_error("%s:%d: %s", __FILE__, __LINE__, msg); return (code); }          \
+  } while (0)
+
+// Stream-ordered scratch allocation (cudaMallocAsync on the device's default pool with the release threshold
+// raised to "never"): after warm-up the proving path performs no cudaMalloc / cudaFree and no host sync for
+// temporaries (the reference does one of each per operator, fr-tensor.cu:92-113).
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s);
+int scratch_free(void* p, cudaStream_t s);
+
+struct Scratch {                       // RAII helper used inside the C-ABI functions
+  void* p = nullptr; cudaStream_t s = 0;
+  ~Scratch() { if (p) scratch_free(p, s); }
+  int alloc(size_t bytes, cudaStream_t st) { s = st; return scratch_alloc(&p, bytes ? bytes : 16, st); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+int num_sms();
+
+#if defined(__CUDACC__)
+// ---- block-wide modular sum of `cnt` Fr values per thread (cnt <= 3); result valid in thread 0.
+template <int CNT>
+__device__ __forceinline__ void block_reduce_fr(Fr* vals, Fr* smem /* CNT * 32 */) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int c = 0; c < CNT; ++c) {
+      Fr o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, vals[c].v[i], off);
+      vals[c] = add(vals[c], o);
+    }
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CNT; ++c) smem[c * 32 + warp] = vals[c];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int c = 0; c < CNT; ++c) vals[c] = (lane < nwarps) ? smem[c * 32 + lane] : Fr::zero();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int c = 0; c < CNT; ++c) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, vals[c].v[i], off);
+        vals[c] = add(vals[c], o);
+      }
+    }
+  }
+}
+#endif
+
+}  // namespace zk

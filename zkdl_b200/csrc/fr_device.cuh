@@ -1,0 +1,86 @@
+// fr_device.cuh — per-element math of the Fr kernels as host/device functions, so the CPU test-suite can run the
+// exact code the kernels instantiate (tests/host_shim.cpp) against the oracle.
+#pragma once
+#include <math.h>
+#include "field.cuh"
+
+namespace zk {
+
+// Fr_me_step / Fr_partial_me_step pair rule (/root/reference/fr-tensor.cu:404-408): a0 + x (a1 - a0); a missing a1 is 0,
+// for which the reference's a0 - x*a0 is the same field element.
+ZK_HD Fr fold_pair(const Fr& a0, const Fr& a1, const Fr& x) { return add(a0, mul(x, sub(a1, a0))); }
+
+// Fr_ip_sc_step coefficients (/root/reference/proof.cu:55-70), optionally pre-weighted by e (Hadamard sumcheck,
+// proof.cu:120-129 evaluates the three coefficient vectors at u[1:], i.e. an eq-weighted sum), plus the two folds.
+//   c0 = a0 b0, c1 = a0 (b1-b0) + b0 (a1-a0), c2 = (a1-a0)(b1-b0);   c1 via a1 b1 - c0 - c2 (3 products instead of 4)
+template <bool WEIGHTED>
+ZK_HD void ip_pair(const Fr& a0, const Fr& a1, const Fr& b0, const Fr& b1, const Fr& e, const Fr& x, Fr* c, Fr& a_out, Fr& b_out) {
+  Fr da = sub(a1, a0), db = sub(b1, b0);
+  Fr wa0 = WEIGHTED ? mul(e, a0) : a0;
+  Fr wda = WEIGHTED ? mul(e, da) : da;
+  c[0] = mul(wa0, b0);
+  c[2] = mul(wda, db);
+  Fr t = mul(add(wa0, wda), b1);
+  c[1] = sub(sub(t, c[0]), c[2]);
+  a_out = add(a0, mul(x, da));
+  b_out = add(b0, mul(x, db));
+}
+
+// Fr_bin_sc_step coefficients (/root/reference/proof.cu:152-163) weighted by e, plus the fold with x:
+//   c0 = a0^2 - a0 = a0 (a0 - 1), c1 = 2 a0 d - d = d (2 a0 - 1), c2 = d^2, d = a1 - a0
+ZK_HD Fr bin_pair(const Fr& a0, const Fr& a1, const Fr& e, const Fr& x, Fr* c) {
+  Fr d = sub(a1, a0);
+  Fr ea0 = mul(e, a0), ed = mul(e, d);
+  Fr one = Fr::one();
+  c[0] = mul(ea0, sub(a0, one));
+  c[1] = mul(ed, sub(dbl(a0), one));
+  c[2] = mul(ed, d);
+  return add(a0, mul(x, d));
+}
+
+// float_to_Fr (/root/reference/zkfc.cu:63-78): round-half-away(|x| * 2^16) as u32 (saturating, NaN -> 0), sign from the
+// sign bit; NOT Montgomery.
+ZK_HD Fr float_to_fr(float x) {
+  x = x * 65536.0f;
+  float ax = roundf(fabsf(x));
+  bool negative = signbit(x);
+  uint32_t v;
+#if defined(__CUDA_ARCH__)
+  v = __float2uint_rz(ax);
+#else
+  if (ax != ax) v = 0; else if (ax >= 4294967296.0f) v = 0xffffffffu; else v = (uint32_t)ax;
+#endif
+  Fr r = Fr::zero(); r.v[0] = v;
+  return negative ? sub(Fr::zero(), r) : r;
+}
+
+// relu_kernel decomposition (/root/reference/zkrelu.cu:11-41)
+struct ReluParts { uint32_t q; uint16_t r; bool positive; bool out_of_range; };
+ZK_HD ReluParts relu_decompose(const Fr& X) {
+  Fr x = from_mont(X);
+  ReluParts p; p.positive = false; p.out_of_range = false;
+  uint64_t mag = 0;
+  bool hi_zero = (x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7]) == 0;
+  if (hi_zero && x.v[1] <= 32767u) {                        // x <= 2^47 - 1
+    p.positive = true;
+    mag = (uint64_t)x.v[0] | ((uint64_t)x.v[1] << 32);
+  } else {
+    Fr lim = Fr::modulus();                                 // p - 2^47 = {1, 0xffff7fff, p2, ...} (zkrelu.cu:23)
+    lim.v[1] -= 32768u;
+    if (gte(x, lim)) {
+      Fr t = Fr::zero(); t.v[1] = 32768u;
+      Fr s = add(x, t);                                     // x + 2^47 - p = 2^47 - |x|
+      mag = (uint64_t)s.v[0] | ((uint64_t)s.v[1] << 32);
+    } else {
+      p.out_of_range = true;                                // undefined in the reference (uninitialised mag/sign)
+    }
+  }
+  bool rem_sign = (mag & 32768ull) != 0;
+  uint32_t rem_mag = (uint32_t)(mag & 32767ull);
+  int32_t rem = rem_sign ? (int32_t)rem_mag - 32768 : (int32_t)rem_mag;
+  p.q = (uint32_t)((mag - (uint64_t)(int64_t)rem) >> 16);
+  p.r = (uint16_t)(rem_mag | (rem_sign ? 0x8000u : 0u));
+  return p;
+}
+
+}  // namespace zk

@@ -1,0 +1,528 @@
+// fr_kernels.cu — Fr tensor kernels: elementwise ops, multilinear folds, the three sumchecks, quantisation,
+// Fr matmul and the ReLU decomposition.  sm_100a, integer pipes only (no tensor cores: nothing here is a dense
+// floating-point contraction).
+//
+// Replaces /root/reference/fr-tensor.cu (elementwise, Fr_sum_reduction, Fr_me_step, Fr_partial_me_step),
+// proof.cu (Fr_ip_sc_step, Fr_bin_sc_step and the host recursions), zkfc.cu (float_to_Fr_kernel,
+// matrixMultiplyOptimized) and zkrelu.cu (relu_kernel).
+//
+// Design: every sumcheck round is ONE streaming pass that reads the table(s), writes the folded
+// table(s) and accumulates that round's three (eq-weighted) coefficients; the reference makes ~10 passes and
+// O(log n) extra launches per round.  Multilinear evaluation folds three variables per pass.  Once a table has
+// <= TAIL_N entries a single-CTA kernel finishes all remaining rounds without further launches.
+#include <atomic>
+#include "common.cuh"
+#include "fr_device.cuh"
+#include "../../include/zkdl_b200.h"
+
+namespace zk {
+extern std::atomic<uint64_t> g_launches;
+#define ZK_LAUNCH(...)            \
+  do {                            \
+    __VA_ARGS__;                  \
+    zk::g_launches.fetch_add(1);  \
+    ZK_CHECK_LAUNCH();            \
+  } while (0)
+
+static constexpr int THREADS = 256;
+static constexpr size_t TAIL_N = 2048;        // tables this small finish in one single-CTA launch
+static constexpr int TAIL_THREADS = 512;
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const Fr* F(const zkdl_fr_t* p) { return reinterpret_cast<const Fr*>(p); }
+static inline Fr* F(zkdl_fr_t* p) { return reinterpret_cast<Fr*>(p); }
+static inline Fr host_fr(const zkdl_fr_t* p) { Fr r; for (int i = 0; i < 8; ++i) r.v[i] = p->val[i]; return r; }
+
+static inline unsigned stream_grid(size_t work_items, int threads) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * 8;                       // grid sized in multiples of the SM count
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+template <int OP>
+__global__ void __launch_bounds__(THREADS) k_fr_elementwise(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = a[i], r;
+    if (OP == ZKDL_OP_ADD) r = add(x, b[i]);
+    else if (OP == ZKDL_OP_SUB) r = sub(x, b[i]);
+    else if (OP == ZKDL_OP_MUL) r = mul(x, b[i]);
+    else if (OP == ZKDL_OP_NEG) r = neg(x);
+    else if (OP == ZKDL_OP_MONT) r = to_mont(x);
+    else r = from_mont(x);
+    out[i] = r;
+  }
+}
+template <int OP>
+__global__ void __launch_bounds__(THREADS) k_fr_broadcast(const Fr* __restrict__ a, Fr x, Fr* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v = a[i], r;
+    if (OP == ZKDL_OP_ADD) r = add(v, x);
+    else if (OP == ZKDL_OP_SUB) r = sub(v, x);
+    else r = mul(v, x);
+    out[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sums
+// partials[blockIdx.x * CNT + c]; then k_fr_sum_final reduces `nparts` rows of CNT values.
+__global__ void __launch_bounds__(THREADS) k_fr_sum_partial(const Fr* __restrict__ a, size_t n, Fr* __restrict__ partials) {
+  __shared__ Fr sm[32];
+  Fr acc = Fr::zero();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = add(acc, a[i]);
+  block_reduce_fr<1>(&acc, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+template <int CNT>
+__global__ void __launch_bounds__(TAIL_THREADS) k_fr_sum_final(const Fr* __restrict__ partials, unsigned nparts, Fr* __restrict__ out) {
+  __shared__ Fr sm[CNT * 32];
+  Fr acc[CNT];
+#pragma unroll
+  for (int c = 0; c < CNT; ++c) acc[c] = Fr::zero();
+  for (unsigned i = threadIdx.x; i < nparts; i += blockDim.x)
+#pragma unroll
+    for (int c = 0; c < CNT; ++c) acc[c] = add(acc[c], partials[(size_t)i * CNT + c]);
+  block_reduce_fr<CNT>(acc, sm);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int c = 0; c < CNT; ++c) out[c] = acc[c];
+}
+
+// ------------------------------------------------------------------------------------------------ folds
+// R fold rounds in one pass over rows of `window` columns: out[r', c] = fold_R(in[r' * 2^R + 0..2^R-1, c]);
+// window == 1 is Fr_me_step applied R times, window > 1 is Fr_partial_me_step applied R times.  Missing rows are 0.
+template <int R>
+__global__ void __launch_bounds__(THREADS) k_fr_fold_multi(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict__ xs,
+                                                           size_t in_size, size_t out_rows, size_t window) {
+  Fr x[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) x[r] = xs[r];
+  const size_t total = out_rows * window;
+  for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+    size_t row = gid / window, col = gid - row * window;
+    Fr v[1 << R];
+#pragma unroll
+    for (int t = 0; t < (1 << R); ++t) {
+      size_t idx = ((row << R) + t) * window + col;
+      v[t] = idx < in_size ? in[idx] : Fr::zero();
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int t = 0; t < (1 << (R - 1 - r)); ++t) v[t] = fold_pair(v[2 * t], v[2 * t + 1], x[r]);
+    out[gid] = v[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ eq tables
+// E[i] = prod_j (bit_j(i) ? q[j] : 1 - q[j]), i < 2^t  (q[0] binds the least-significant index bit).
+// rev = 1 swaps the two factors (used for the generator weights of me_open).
+__global__ void __launch_bounds__(TAIL_THREADS) k_eq_small(const Fr* __restrict__ q, int t, int rev, Fr* __restrict__ E) {
+  // single CTA, levels 0..t-1, t <= 11 handled with TAIL_THREADS threads looping
+  if (threadIdx.x == 0) E[0] = Fr::one();
+  __syncthreads();
+  for (int j = 0; j < t; ++j) {
+    Fr qj = q[j];
+    size_t half = (size_t)1 << j;
+    for (size_t i = threadIdx.x; i < half; i += blockDim.x) {
+      Fr e = E[i];
+      Fr hi = mul(e, qj), lo = sub(e, hi);
+      if (rev) { E[i] = hi; E[i + half] = lo; } else { E[i] = lo; E[i + half] = hi; }
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(THREADS) k_eq_level(Fr* __restrict__ E, Fr qj, size_t half, int rev) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
+    Fr e = E[i];
+    Fr hi = mul(e, qj), lo = sub(e, hi);
+    if (rev) { E[i] = hi; E[i + half] = lo; } else { E[i] = lo; E[i + half] = hi; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ sumcheck rounds
+enum { SC_IP = 0, SC_HP = 1, SC_BIN = 2 };
+
+// One round over the pairs handled by this thread; accumulates the three coefficient sums into acc[3].
+// h indexes double-pairs so that the eq table for the next round (E'[h] = E[2h] + E[2h+1]) is produced in the same pass.
+template <int KIND>
+__device__ __forceinline__ void sc_round_items(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
+                                               const Fr* __restrict__ e_in, Fr* __restrict__ e_out, const Fr& x, size_t in_size, size_t out_size,
+                                               size_t H, size_t h0, size_t hstride, Fr* acc) {
+  for (size_t h = h0; h < H; h += hstride) {
+    Fr e0, e1;
+    if (KIND != SC_IP) {
+      e0 = e_in[2 * h];
+      if (e_out) { e1 = e_in[2 * h + 1]; e_out[h] = add(e0, e1); } else e1 = Fr::zero();
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      size_t g = 2 * h + t;
+      if (g >= out_size) break;
+      size_t g0 = 2 * g, g1 = 2 * g + 1;
+      Fr a0 = g0 < in_size ? a[g0] : Fr::zero();
+      Fr a1 = g1 < in_size ? a[g1] : Fr::zero();
+      Fr c[3];
+      if (KIND == SC_BIN) {
+        const Fr& e = t ? e1 : e0;
+        a_out[g] = bin_pair(a0, a1, e, x, c);
+      } else {
+        Fr b0 = g0 < in_size ? b[g0] : Fr::zero();
+        Fr b1 = g1 < in_size ? b[g1] : Fr::zero();
+        if (KIND == SC_HP) {
+          const Fr& e = t ? e1 : e0;
+          ip_pair<true>(a0, a1, b0, b1, e, x, c, a_out[g], b_out[g]);
+        } else {
+          ip_pair<false>(a0, a1, b0, b1, a0, x, c, a_out[g], b_out[g]);
+        }
+      }
+      acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
+    }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
+                                                      const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x, size_t in_size, size_t out_size,
+                                                      size_t H, Fr* __restrict__ partials) {
+  __shared__ Fr sm[3 * 32];
+  Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+  sc_round_items<KIND>(a, b, a_out, b_out, e_in, e_out, x, in_size, out_size, H,
+                       blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, acc);
+  block_reduce_fr<3>(acc, sm);
+  if (threadIdx.x == 0) { partials[blockIdx.x * 3 + 0] = acc[0]; partials[blockIdx.x * 3 + 1] = acc[1]; partials[blockIdx.x * 3 + 2] = acc[2]; }
+}
+
+// All remaining rounds in one CTA.  bufs: a0/a1 (and b0/b1) ping-pong, e0/e1 ping-pong.  xs = fold challenges for the
+// remaining rounds.  proof gets 3 values per round, then the final a[0] (and b[0]).
+template <int KIND>
+__global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(Fr* a0, Fr* a1, Fr* b0, Fr* b1, Fr* e0, Fr* e1, const Fr* __restrict__ xs,
+                                                          int rounds, size_t in_size, size_t esize, Fr* __restrict__ proof) {
+  __shared__ Fr sm[3 * 32];
+  Fr *a = a0, *an = a1, *b = b0, *bn = b1, *e = e0, *en = e1;
+  for (int j = 0; j < rounds; ++j) {
+    size_t out_size = (in_size + 1) / 2;
+    size_t H = (KIND != SC_IP && esize >= 2) ? esize / 2 : (out_size + 1) / 2;
+    Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+    Fr x = xs[j];
+    sc_round_items<KIND>(a, b, an, bn, e, (KIND != SC_IP && esize >= 2) ? en : nullptr, x, in_size, out_size, H, threadIdx.x, blockDim.x, acc);
+    block_reduce_fr<3>(acc, sm);
+    if (threadIdx.x == 0) { proof[3 * j] = acc[0]; proof[3 * j + 1] = acc[1]; proof[3 * j + 2] = acc[2]; }
+    __syncthreads();
+    Fr* t = a; a = an; an = t; t = b; b = bn; bn = t; t = e; e = en; en = t;
+    in_size = out_size; esize = esize >= 2 ? esize / 2 : 1;
+  }
+  if (threadIdx.x == 0) {
+    proof[3 * rounds] = a[0];
+    if (KIND != SC_BIN) proof[3 * rounds + 1] = b[0];
+  }
+}
+
+// fold tail for plain evaluation: remaining rounds of Fr_me in one CTA (window 1)
+__global__ void __launch_bounds__(TAIL_THREADS) k_fold_tail(Fr* a0, Fr* a1, const Fr* __restrict__ xs, int rounds, size_t in_size, Fr* __restrict__ out) {
+  Fr *a = a0, *an = a1;
+  for (int j = 0; j < rounds; ++j) {
+    size_t out_size = (in_size + 1) / 2;
+    Fr x = xs[j];
+    for (size_t g = threadIdx.x; g < out_size; g += blockDim.x) {
+      Fr v0 = a[2 * g];
+      Fr v1 = 2 * g + 1 < in_size ? a[2 * g + 1] : Fr::zero();
+      an[g] = fold_pair(v0, v1, x);
+    }
+    __syncthreads();
+    Fr* t = a; a = an; an = t;
+    in_size = out_size;
+  }
+  if (threadIdx.x == 0) out[0] = a[0];
+}
+
+// ------------------------------------------------------------------------------------------------ quantise / matmul / relu
+__global__ void __launch_bounds__(THREADS) k_float_to_fr(const float* __restrict__ fs, Fr* __restrict__ out, uint32_t rows_in, uint32_t rows_out,
+                                                         uint32_t cols_in, uint32_t cols_out) {
+  size_t total = (size_t)rows_out * cols_out;
+  for (size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x; gid < total; gid += (size_t)gridDim.x * blockDim.x) {
+    uint32_t r = (uint32_t)(gid / cols_out), c = (uint32_t)(gid - (size_t)r * cols_out);
+    out[gid] = (r < rows_in && c < cols_in) ? float_to_fr(fs[(size_t)r * cols_in + c]) : Fr::zero();
+  }
+}
+
+static constexpr int MM_TILE = 16;
+// C = A * B over Fr; 16x16 output tile per CTA, K-tiles staged through shared memory.
+__global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
+                                                                 size_t rowsA, size_t colsA, size_t colsB) {
+  __shared__ Fr As[MM_TILE][MM_TILE];
+  __shared__ Fr Bs[MM_TILE][MM_TILE];
+  const int tx = threadIdx.x % MM_TILE, ty = threadIdx.x / MM_TILE;
+  const size_t row = (size_t)blockIdx.y * MM_TILE + ty, col = (size_t)blockIdx.x * MM_TILE + tx;
+  Fr sum = Fr::zero();
+  for (size_t k0 = 0; k0 < colsA; k0 += MM_TILE) {
+    As[ty][tx] = (row < rowsA && k0 + tx < colsA) ? A[row * colsA + k0 + tx] : Fr::zero();
+    Bs[ty][tx] = (k0 + ty < colsA && col < colsB) ? B[(k0 + ty) * colsB + col] : Fr::zero();
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < MM_TILE; ++k) sum = add(sum, mul(As[ty][k], Bs[k][tx]));
+    __syncthreads();
+  }
+  if (row < rowsA && col < colsB) C[row * colsB + col] = sum;
+}
+
+// relu: Z, sign and the packed decomposition (q: u32 rescaled magnitude, r: u16 = rem_mag | rem_sign << 15)
+__global__ void __launch_bounds__(THREADS) k_relu(const Fr* __restrict__ X, Fr* __restrict__ Z, Fr* __restrict__ sign, uint32_t* __restrict__ qpk,
+                                                  uint16_t* __restrict__ rpk, size_t n, uint32_t* __restrict__ bad) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    ReluParts p = relu_decompose(X[i]);
+    if (p.out_of_range && bad) atomicAdd(bad, 1u);
+    sign[i] = p.positive ? Fr::one() : Fr::zero();
+    Fr q = Fr::zero(); q.v[0] = p.q;
+    Z[i] = p.positive ? to_mont(q) : Fr::zero();             // mont(q) * sign  (zkrelu.cu:40)
+    qpk[i] = p.q; rpk[i] = p.r;
+  }
+}
+// expand packed bits into the reference's 0/1 Fr tables: cell c -> element c / BITS, bit c % BITS (coalesced 32 B stores)
+template <int BITS, class T>
+__global__ void __launch_bounds__(THREADS) k_expand_bits(const T* __restrict__ packed, Fr* __restrict__ out, size_t ncells) {
+  const Fr one = Fr::one(), zero = Fr::zero();
+  for (size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x; c < ncells; c += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w = packed[c / BITS];
+    out[c] = ((w >> (c % BITS)) & 1u) ? one : zero;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host-side drivers
+static int upload_frs(const zkdl_fr_t* host, size_t k, Scratch& buf, cudaStream_t st) {
+  int rc = buf.alloc(sizeof(Fr) * (k ? k : 1), st);
+  if (rc) return rc;
+  if (k) ZK_CUDA(cudaMemcpyAsync(buf.p, host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  return ZK_OK;
+}
+
+// builds E over q[0..t-1] (device) into E (2^t entries)
+int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st) {
+  int small = t < 11 ? t : 11;
+  ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, small, rev, E));
+  for (int j = small; j < t; ++j) {
+    size_t half = (size_t)1 << j;
+    ZK_LAUNCH(k_eq_level<<<stream_grid(half, THREADS), THREADS, 0, st>>>(E, host_fr(q_host + j), half, rev));
+  }
+  return ZK_OK;
+}
+
+// Fr_me / Fr_partial_me driver: folds `k` rounds with window `w`; result (out_n entries) copied to out.
+static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t w, Fr* out, cudaStream_t st) {
+  if (k == 0) { ZK_CUDA(cudaMemcpyAsync(out, a, sizeof(Fr) * n, cudaMemcpyDeviceToDevice, st)); return ZK_OK; }
+  Scratch xs; int rc = upload_frs(u_host, k, xs, st); if (rc) return rc;
+  size_t rows = (n + w - 1) / w;                      // partial trailing row is zero padded by index tests
+  Scratch bufA, bufB;
+  size_t cap = ((rows + 1) / 2) * w;
+  if ((rc = bufA.alloc(sizeof(Fr) * cap, st))) return rc;
+  if ((rc = bufB.alloc(sizeof(Fr) * cap, st))) return rc;
+  const Fr* cur = a; size_t cur_n = n;
+  Fr* bufs[2] = {bufA.as<Fr>(), bufB.as<Fr>()}; int which = 0;
+  size_t j = 0;
+  while (j < k) {
+    size_t left = k - j;
+    if (w == 1 && cur_n <= TAIL_N && cur != a) {        // finish in one CTA (needs a writable current buffer)
+      Scratch res; if ((rc = res.alloc(sizeof(Fr), st))) return rc;
+      ZK_LAUNCH(k_fold_tail<<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(cur), bufs[which], xs.as<Fr>() + j, (int)left, cur_n, res.as<Fr>()));
+      ZK_CUDA(cudaMemcpyAsync(out, res.p, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+      return ZK_OK;
+    }
+    int R = left >= 3 ? 3 : (left == 2 ? 2 : 1);
+    size_t out_rows = rows;
+    for (int r = 0; r < R; ++r) out_rows = (out_rows + 1) / 2;
+    Fr* dst = bufs[which];
+    size_t total = out_rows * w;
+    unsigned grid = stream_grid(total, THREADS);
+    if (R == 3) ZK_LAUNCH(k_fr_fold_multi<3><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
+    else if (R == 2) ZK_LAUNCH(k_fr_fold_multi<2><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
+    else ZK_LAUNCH(k_fr_fold_multi<1><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
+    cur = dst; cur_n = total; rows = out_rows; which ^= 1; j += R;
+  }
+  ZK_CUDA(cudaMemcpyAsync(out, cur, sizeof(Fr) * cur_n, cudaMemcpyDeviceToDevice, st));
+  return ZK_OK;
+}
+
+template <int KIND>
+static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, Fr* proof, cudaStream_t st) {
+  // fold challenges: IP folds with u, HP/BIN fold with v and weight with eq(u[1:])
+  const zkdl_fr_t* fold_host = (KIND == SC_IP) ? u_host : v_host;
+  int rc;
+  if (k == 0) {                                           // proof.cu:75-79 / 114-118 / 168-171
+    ZK_CUDA(cudaMemcpyAsync(proof, a, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    if (KIND != SC_BIN) ZK_CUDA(cudaMemcpyAsync(proof + 1, b, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    return ZK_OK;
+  }
+  Scratch xs; if ((rc = upload_frs(fold_host, k, xs, st))) return rc;
+  Scratch uq, E0, E1;
+  size_t esize = 1;
+  if (KIND != SC_IP) {
+    esize = (size_t)1 << (k - 1);
+    if ((rc = upload_frs(u_host + 1, k - 1, uq, st))) return rc;
+    if ((rc = E0.alloc(sizeof(Fr) * esize, st))) return rc;
+    if ((rc = E1.alloc(sizeof(Fr) * (esize / 2 + 1), st))) return rc;
+    if ((rc = build_eq_table(uq.as<Fr>(), u_host + 1, (int)k - 1, 0, E0.as<Fr>(), st))) return rc;
+  }
+  size_t half = (n + 1) / 2;
+  Scratch A0, A1, B0, B1, parts;
+  if ((rc = A0.alloc(sizeof(Fr) * half, st))) return rc;
+  if ((rc = A1.alloc(sizeof(Fr) * half, st))) return rc;
+  if (KIND != SC_BIN) { if ((rc = B0.alloc(sizeof(Fr) * half, st))) return rc; if ((rc = B1.alloc(sizeof(Fr) * half, st))) return rc; }
+  unsigned maxgrid = stream_grid((half + 1) / 2, THREADS);
+  if ((rc = parts.alloc(sizeof(Fr) * 3 * maxgrid, st))) return rc;
+
+  const Fr *ca = a, *cb = b; size_t cur_n = n;
+  Fr *abuf[2] = {A0.as<Fr>(), A1.as<Fr>()}, *bbuf[2] = {B0.as<Fr>(), B1.as<Fr>()};
+  Fr* ebuf[2] = {E0.as<Fr>(), E1.as<Fr>()};
+  int which = 0, ewhich = 0;
+  size_t j = 0;
+  for (; j < k; ++j) {
+    if (cur_n <= TAIL_N && j > 0) break;                  // tail needs writable ping-pong buffers: at least one round done
+    size_t out_size = (cur_n + 1) / 2;
+    bool fold_e = (KIND != SC_IP) && esize >= 2;
+    size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
+    unsigned grid = stream_grid(H, THREADS);
+    ZK_LAUNCH(k_sc_round<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
+                                                         host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>()));
+    ZK_LAUNCH(k_fr_sum_final<3><<<1, TAIL_THREADS, 0, st>>>(parts.as<Fr>(), grid, proof + 3 * j));
+    ca = abuf[which]; cb = bbuf[which]; which ^= 1; cur_n = out_size;
+    if (fold_e) { ewhich ^= 1; esize /= 2; }
+  }
+  if (j < k) {
+    ZK_LAUNCH(k_sc_tail<KIND><<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(ca), abuf[which], const_cast<Fr*>(cb), bbuf[which], ebuf[ewhich], ebuf[ewhich ^ 1],
+                                                          xs.as<Fr>() + j, (int)(k - j), cur_n, esize, proof + 3 * j));
+  } else {
+    ZK_CUDA(cudaMemcpyAsync(proof + 3 * k, ca, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    if (KIND != SC_BIN) ZK_CUDA(cudaMemcpyAsync(proof + 3 * k + 1, cb, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+  }
+  return ZK_OK;
+}
+
+// exposed to msm.cu / prove.cu
+int fr_partial_me_dev(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t w, Fr* out, cudaStream_t st) {
+  return fold_driver(a, n, u_host, k, w, out, st);
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int zkdl_fr_elementwise(int op, const zkdl_fr_t* a, const zkdl_fr_t* b, zkdl_fr_t* out, size_t n, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_REQUIRE(a && out, ZK_ERR_ARG, "null tensor");
+  if (op <= ZKDL_OP_MUL) ZK_REQUIRE(b, ZK_ERR_ARG, "binary op needs b");
+  unsigned grid = stream_grid(n, THREADS); cudaStream_t st = S(stream);
+  switch (op) {
+    case ZKDL_OP_ADD: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_ADD><<<grid, THREADS, 0, st>>>(F(a), F(b), F(out), n)); break;
+    case ZKDL_OP_SUB: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_SUB><<<grid, THREADS, 0, st>>>(F(a), F(b), F(out), n)); break;
+    case ZKDL_OP_MUL: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_MUL><<<grid, THREADS, 0, st>>>(F(a), F(b), F(out), n)); break;
+    case ZKDL_OP_NEG: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_NEG><<<grid, THREADS, 0, st>>>(F(a), F(a), F(out), n)); break;
+    case ZKDL_OP_MONT: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_MONT><<<grid, THREADS, 0, st>>>(F(a), F(a), F(out), n)); break;
+    case ZKDL_OP_UNMONT: ZK_LAUNCH(k_fr_elementwise<ZKDL_OP_UNMONT><<<grid, THREADS, 0, st>>>(F(a), F(a), F(out), n)); break;
+    default: ZK_REQUIRE(false, ZK_ERR_ARG, "bad op");
+  }
+  return ZK_OK;
+}
+
+int zkdl_fr_broadcast(int op, const zkdl_fr_t* a, const zkdl_fr_t* x_host, zkdl_fr_t* out, size_t n, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_REQUIRE(a && out && x_host, ZK_ERR_ARG, "null tensor");
+  unsigned grid = stream_grid(n, THREADS); cudaStream_t st = S(stream); Fr x = host_fr(x_host);
+  switch (op) {
+    case ZKDL_OP_ADD: ZK_LAUNCH(k_fr_broadcast<ZKDL_OP_ADD><<<grid, THREADS, 0, st>>>(F(a), x, F(out), n)); break;
+    case ZKDL_OP_SUB: ZK_LAUNCH(k_fr_broadcast<ZKDL_OP_SUB><<<grid, THREADS, 0, st>>>(F(a), x, F(out), n)); break;
+    case ZKDL_OP_MUL: ZK_LAUNCH(k_fr_broadcast<ZKDL_OP_MUL><<<grid, THREADS, 0, st>>>(F(a), x, F(out), n)); break;
+    default: ZK_REQUIRE(false, ZK_ERR_ARG, "bad op");
+  }
+  return ZK_OK;
+}
+
+int zkdl_fr_sum(const zkdl_fr_t* a, size_t n, zkdl_fr_t* out, void* stream) {
+  cudaStream_t st = S(stream);
+  ZK_REQUIRE(out, ZK_ERR_ARG, "null out");
+  if (n == 0) { ZK_CUDA(cudaMemsetAsync(out, 0, sizeof(Fr), st)); return ZK_OK; }
+  unsigned grid = stream_grid(n, THREADS); if (grid > 1024) grid = 1024;
+  Scratch parts; int rc = parts.alloc(sizeof(Fr) * grid, st); if (rc) return rc;
+  ZK_LAUNCH(k_fr_sum_partial<<<grid, THREADS, 0, st>>>(F(a), n, parts.as<Fr>()));
+  ZK_LAUNCH(k_fr_sum_final<1><<<1, TAIL_THREADS, 0, st>>>(parts.as<Fr>(), grid, F(out)));
+  return ZK_OK;
+}
+
+int zkdl_fr_fold(const zkdl_fr_t* in, zkdl_fr_t* out, const zkdl_fr_t* x_host, size_t in_size, void* stream) {
+  return zkdl_fr_partial_fold(in, out, x_host, in_size, 1, stream);
+}
+
+int zkdl_fr_partial_fold(const zkdl_fr_t* in, zkdl_fr_t* out, const zkdl_fr_t* x_host, size_t in_size, size_t window, void* stream) {
+  cudaStream_t st = S(stream);
+  ZK_REQUIRE(window >= 1, ZK_ERR_ARG, "window must be >= 1");
+  if (in_size == 0) return ZK_OK;
+  Scratch xs; int rc = upload_frs(x_host, 1, xs, st); if (rc) return rc;
+  size_t out_rows = (in_size + 2 * window - 1) / (2 * window);
+  ZK_LAUNCH(k_fr_fold_multi<1><<<stream_grid(out_rows * window, THREADS), THREADS, 0, st>>>(F(in), F(out), xs.as<Fr>(), in_size, out_rows, window));
+  return ZK_OK;
+}
+
+int zkdl_fr_me(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, zkdl_fr_t* out, void* stream) {
+  // FrTensor::operator()(u) guard (fr-tensor.cu:295-300)
+  ZK_REQUIRE(k < 32 && !(n <= (((size_t)1 << k) / 2) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");
+  if (k == 0) { ZK_CUDA(cudaMemcpyAsync(out, a, sizeof(Fr), cudaMemcpyDeviceToDevice, S(stream))); return ZK_OK; }
+  return fold_driver(F(a), n, u_host, k, 1, F(out), S(stream));
+}
+
+size_t zkdl_partial_me_size(size_t n, size_t k, size_t window) {
+  size_t sz = n;
+  for (size_t j = 0; j < k; ++j) sz = window * ((sz + 2 * window - 1) / (2 * window));
+  return sz;
+}
+
+int zkdl_fr_partial_me(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t window, zkdl_fr_t* out, void* stream) {
+  ZK_REQUIRE(window >= 1, ZK_ERR_ARG, "window must be >= 1");
+  // fr-tensor.cu:370-374 guard; k == 0 is the reference's (benign) undefined shift: treated as a copy
+  if (k > 0) ZK_REQUIRE(k < 40 && n > window * ((size_t)1 << (k - 1)), ZK_ERR_DIM, "Incompatible dimensions");
+  // the multi-round kernel needs whole rows except for a zero-padded tail, which the index tests provide
+  return fold_driver(F(a), n, u_host, k, window, F(out), S(stream));
+}
+
+int zkdl_ip_sumcheck(const zkdl_fr_t* a, const zkdl_fr_t* b, size_t n, const zkdl_fr_t* u_host, size_t k, zkdl_fr_t* proof, void* stream) {
+  ZK_REQUIRE(k < 32 && !(n <= (((size_t)1 << k) / 2) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");   // proof.cu:102-104
+  return sumcheck_driver<SC_IP>(F(a), F(b), n, u_host, nullptr, k, F(proof), S(stream));
+}
+int zkdl_hp_sumcheck(const zkdl_fr_t* a, const zkdl_fr_t* b, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, zkdl_fr_t* proof, void* stream) {
+  ZK_REQUIRE(k >= 1 && k < 32 && !(n <= ((size_t)1 << (k - 1)) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");  // proof.cu:143-147
+  return sumcheck_driver<SC_HP>(F(a), F(b), n, u_host, v_host, k, F(proof), S(stream));
+}
+int zkdl_bin_sumcheck(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, zkdl_fr_t* proof, void* stream) {
+  ZK_REQUIRE(k < 32 && !(n <= (((size_t)1 << k) / 2) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");   // proof.cu:193-196
+  return sumcheck_driver<SC_BIN>(F(a), nullptr, n, u_host, v_host, k, F(proof), S(stream));
+}
+
+int zkdl_float_to_fr(const float* fs, zkdl_fr_t* out, uint32_t rows_in, uint32_t rows_out, uint32_t cols_in, uint32_t cols_out, void* stream) {
+  size_t total = (size_t)rows_out * cols_out;
+  if (total == 0) return ZK_OK;
+  ZK_LAUNCH(k_float_to_fr<<<stream_grid(total, THREADS), THREADS, 0, S(stream)>>>(fs, F(out), rows_in, rows_out, cols_in, cols_out));
+  return ZK_OK;
+}
+
+int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t rowsA, size_t colsA, size_t colsB, void* stream) {
+  if (rowsA == 0 || colsB == 0) return ZK_OK;
+  dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
+  ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, S(stream)>>>(F(A), F(B), F(C), rowsA, colsA, colsB));
+  return ZK_OK;
+}
+
+int zkdl_relu(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, uint32_t* out_of_range, void* stream) {
+  cudaStream_t st = S(stream);
+  if (n == 0) return ZK_OK;
+  Scratch qpk, rpk; int rc;
+  if ((rc = qpk.alloc(sizeof(uint32_t) * n, st))) return rc;
+  if ((rc = rpk.alloc(sizeof(uint16_t) * n, st))) return rc;
+  if (out_of_range) ZK_CUDA(cudaMemsetAsync(out_of_range, 0, sizeof(uint32_t), st));
+  ZK_LAUNCH(k_relu<<<stream_grid(n, THREADS), THREADS, 0, st>>>(F(X), F(Z), F(sign), qpk.as<uint32_t>(), rpk.as<uint16_t>(), n, out_of_range));
+  if (mag_bin) ZK_LAUNCH(k_expand_bits<32, uint32_t><<<stream_grid(n * 32, THREADS), THREADS, 0, st>>>(qpk.as<uint32_t>(), F(mag_bin), n * 32));
+  if (rem_bin) ZK_LAUNCH(k_expand_bits<16, uint16_t><<<stream_grid(n * 16, THREADS), THREADS, 0, st>>>(rpk.as<uint16_t>(), F(rem_bin), n * 16));
+  return ZK_OK;
+}
+
+}  // extern "C"

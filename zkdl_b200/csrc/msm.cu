@@ -1,0 +1,555 @@
+// msm.cu — G1 tensors and the fixed-base batched Pippenger MSM behind Commitment::commit / open / me_open.
+//
+// Replaces /root/reference/g1-tensor.cu (elementwise group ops, G1Jacobian_sum_reduction, the 256-step
+// G1Jacobian_mul ladder, G1_me_step) and /root/reference/commitment.cu (commit via |t| independent ladders +
+// sum_axis_n_optimized; me_open_step with 5 sequential ladders per thread).
+//
+// Design.  A Commitment is a fixed generator set, so zkdl_g1_table_create precomputes affine window
+// tables 2^(4w) G[i] once; every commitment, opening round and commitment-vector evaluation is then a batched
+// Pippenger MSM over those tables with NO doublings on the proving path:
+//   count  : signed-digit recode every scalar (digit width c = 4t), histogram (row, bucket) keys
+//   scan   : exclusive prefix sum of the histogram
+//   scatter: counting sort of (window-table index, sign) entries by key
+//   accum  : S lanes per bucket, XYZZ += affine mixed additions (8M+2S), warp-shuffle combine of the S partials
+//   reduce : one CTA per (row, window-group): sum_k k*B_k by per-thread running sums + shared-memory tree
+//   final  : Horner over window groups (plain mode only) and XYZZ -> Jacobian
+// me_open's log|G| dependent folding rounds are re-expressed as 3*log|G|+1 independent MSMs over the ORIGINAL
+// generators (k_open_scalars computes the per-round scalars), so a whole opening is ONE batched MSM.
+#include <atomic>
+#include "common.cuh"
+#include "g1_device.cuh"
+#include "../../include/zkdl_b200.h"
+
+namespace zk {
+extern std::atomic<uint64_t> g_launches;
+#define ZK_LAUNCH(...)            \
+  do {                            \
+    __VA_ARGS__;                  \
+    zk::g_launches.fetch_add(1);  \
+    ZK_CHECK_LAUNCH();            \
+  } while (0)
+
+int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
+int fr_partial_me_dev(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t w, Fr* out, cudaStream_t st);
+
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static constexpr int G1_THREADS = 128;
+static constexpr int TABLE_C = 4;                 // table window granularity (bits)
+static constexpr int TABLE_W = 64;                // 64 * 4 = 256 bits
+
+static inline unsigned g1_grid(size_t items, int threads) {
+  size_t blocks = (items + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+// ------------------------------------------------------------------------------------------------ elementwise
+__global__ void __launch_bounds__(G1_THREADS) k_g1_elementwise(int op, const G1Jac* __restrict__ a, const void* __restrict__ b, size_t nb,
+                                                               G1Jac* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1Jac pa = a[i];
+    if (op == ZKDL_G1_NEG) { pa.y = neg(pa.y); out[i] = pa; continue; }       // G1Jacobian_minus (g1-tensor.cu:17-19)
+    G1XYZZ acc = xyzz_from_jac(pa);
+    size_t bi = nb == 1 ? 0 : i;
+    if (op == ZKDL_G1_MADD || op == ZKDL_G1_MSUB) {
+      G1Affine pb = reinterpret_cast<const G1Affine*>(b)[bi];
+      xyzz_madd(acc, pb, op == ZKDL_G1_MSUB);
+    } else {
+      G1XYZZ o = xyzz_from_jac(reinterpret_cast<const G1Jac*>(b)[bi]);
+      if (op == ZKDL_G1_SUB) o.y = neg(o.y);
+      acc = xyzz_add(acc, o);
+    }
+    out[i] = xyzz_to_jac(acc);
+  }
+}
+__global__ void __launch_bounds__(G1_THREADS) k_g1_affine_to_jac(const G1Affine* __restrict__ a, G1Jac* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1Jac r; r.x = a[i].x; r.y = a[i].y; r.z = Fq::one(); out[i] = r;         // g1-tensor.cu:142-147
+  }
+}
+// out[i] = [x[i]] P[i mod np]; LSB-first double-and-add over the raw limbs (g1-tensor.cu:422-445), XYZZ arithmetic
+__global__ void __launch_bounds__(G1_THREADS) k_g1_mul(const G1Jac* __restrict__ P, size_t np, const Fr* __restrict__ x, size_t n, G1Jac* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1XYZZ a = xyzz_from_jac(P[i % np]);
+    Fr s = x[i];
+    int top = -1;
+    for (int l = 7; l >= 0; --l) if (s.v[l]) { top = l * 32 + 31 - __clz(s.v[l]); break; }
+    G1XYZZ acc = xyzz_inf();
+    for (int bit = 0; bit <= top; ++bit) {
+      if ((s.v[bit >> 5] >> (bit & 31)) & 1u) acc = xyzz_add(acc, a);
+      if (bit < top) a = xyzz_dbl(a);
+    }
+    out[i] = xyzz_to_jac(acc);
+  }
+}
+
+// block-wide XYZZ tree sum through shared memory; result in thread 0
+__device__ __forceinline__ G1XYZZ block_sum_xyzz(G1XYZZ v, G1XYZZ* sm) {
+  sm[threadIdx.x] = v;
+  __syncthreads();
+  for (unsigned s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = xyzz_add(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  return sm[0];
+}
+extern __shared__ __align__(16) unsigned char g1_dyn_smem[];
+
+__global__ void __launch_bounds__(G1_THREADS) k_g1_sum_partial(const G1Jac* __restrict__ a, size_t n, G1XYZZ* __restrict__ parts) {
+  G1XYZZ* sm = reinterpret_cast<G1XYZZ*>(g1_dyn_smem);
+  G1XYZZ acc = xyzz_inf();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc = xyzz_add(acc, xyzz_from_jac(a[i]));
+  G1XYZZ r = block_sum_xyzz(acc, sm);
+  if (threadIdx.x == 0) parts[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(G1_THREADS) k_g1_sum_final(const G1XYZZ* __restrict__ parts, unsigned nparts, G1Jac* __restrict__ out) {
+  G1XYZZ* sm = reinterpret_cast<G1XYZZ*>(g1_dyn_smem);
+  G1XYZZ acc = xyzz_inf();
+  for (unsigned i = threadIdx.x; i < nparts; i += blockDim.x) acc = xyzz_add(acc, parts[i]);
+  G1XYZZ r = block_sum_xyzz(acc, sm);
+  if (threadIdx.x == 0) out[0] = xyzz_to_jac(r);
+}
+
+// ------------------------------------------------------------------------------------------------ tables
+// tmp[w * n + i] = 2^(TABLE_C * w) * P[i] in XYZZ
+__global__ void __launch_bounds__(G1_THREADS) k_table_expand(const G1Jac* __restrict__ pts, size_t n, int windows, G1XYZZ* __restrict__ tmp) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1XYZZ p = xyzz_from_jac(pts[i]);
+  for (int w = 0; w < windows; ++w) {
+    tmp[(size_t)w * n + i] = p;
+    if (w + 1 < windows)
+      for (int d = 0; d < TABLE_C; ++d) p = xyzz_dbl(p);
+  }
+}
+// XYZZ -> affine with one inversion per CH points (Montgomery's trick); infinity -> (0,0)
+static constexpr int INV_CH = 8;
+__global__ void __launch_bounds__(G1_THREADS) k_batch_affine(const G1XYZZ* __restrict__ in, G1Affine* __restrict__ out, size_t total) {
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t base = t * INV_CH;
+  if (base >= total) return;
+  Fq prod[INV_CH];
+  Fq run = Fq::one();
+#pragma unroll
+  for (int s = 0; s < INV_CH; ++s) {
+    if (base + s < total) { Fq z = in[base + s].zzz; if (!z.is_zero()) run = mul(run, z); }
+    prod[s] = run;
+  }
+  Fq inv = fq_inv(run);
+#pragma unroll
+  for (int s = INV_CH - 1; s >= 0; --s) {
+    if (base + s >= total) continue;
+    G1XYZZ p = in[base + s];
+    if (p.zzz.is_zero()) { G1Affine z; z.x = Fq::zero(); z.y = Fq::zero(); out[base + s] = z; continue; }
+    Fq before = s ? prod[s - 1] : Fq::one();
+    Fq izzz = mul(inv, before);
+    inv = mul(inv, p.zzz);
+    out[base + s] = xyzz_to_affine_with_inv(p, izzz);
+  }
+}
+__global__ void __launch_bounds__(G1_THREADS) k_g1_normalize(const G1Jac* __restrict__ in, G1Jac* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    G1Jac p = in[i];
+    if (is_inf(p)) { out[i] = jac_inf(); continue; }
+    Fq zi = fq_inv(p.z), zi2 = sqr(zi);
+    G1Jac r; r.x = mul(p.x, zi2); r.y = mul(p.y, mul(zi2, zi)); r.z = Fq::one(); out[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MSM pipeline
+struct MsmCfg {
+  size_t n, m;          // bases per row, rows
+  int c, W, K;          // digit width, windows, buckets per group = 2^(c-1)
+  int NG;               // window groups per row: 1 with full tables, W otherwise
+  int full, tstep;      // full tables; table windows per digit window (c / TABLE_C)
+  int mont;             // scalars are Montgomery
+  int S;                // lanes per bucket in the accumulate kernel (power of two <= 32)
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scalars, MsmCfg cfg, uint32_t* __restrict__ counters, uint32_t* __restrict__ entries) {
+  const size_t total = cfg.m * cfg.n;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    size_t row = idx / cfg.n, i = idx - row * cfg.n;
+    Fr mag; bool negative;
+    scalar_prepare(scalars[idx], cfg.mont != 0, mag, negative);
+    if (mag.is_zero()) continue;
+    uint32_t carry = 0;
+    for (int w = 0; w < cfg.W; ++w) {
+      int32_t d = next_digit(mag, w, cfg.c, carry);
+      if (d == 0) continue;
+      uint32_t ad = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      size_t key = (row * cfg.NG + (cfg.full ? 0 : w)) * (size_t)cfg.K + (ad - 1);
+      if (!SCATTER) {
+        atomicAdd(&counters[key], 1u);
+      } else {
+        uint32_t pos = atomicAdd(&counters[key], 1u);
+        uint32_t base = cfg.full ? (uint32_t)((size_t)w * cfg.tstep * cfg.n + i) : (uint32_t)i;
+        entries[pos] = base | ((negative != (d < 0)) ? 0x80000000u : 0u);
+      }
+    }
+  }
+}
+
+// exclusive scan, three phases, tiles of 1024 * 4
+static constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_TILE = SCAN_T * SCAN_PER;
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t wsum[32];
+  unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += y; }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = wsum[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= (unsigned)o) s += y; }
+    wsum[lane] = s;
+  }
+  __syncthreads();
+  uint32_t warp_off = warp ? wsum[warp - 1] : 0;
+  if (total) *total = wsum[31];
+  __syncthreads();
+  return warp_off + x - v;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ tile_sums) {
+  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_PER;
+  uint32_t v[SCAN_PER], s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(s, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_PER; ++k) { if (base + k < n) out[base + k] = off; off += v[k]; }
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_sums(uint32_t* __restrict__ tile_sums, unsigned ntiles, uint32_t* __restrict__ grand_total) {
+  // single block; ntiles may exceed blockDim: serial over chunks
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (unsigned b = 0; b < ntiles; b += SCAN_T) {
+    unsigned i = b + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0, total;
+    uint32_t off = block_exclusive_scan(v, &total);
+    uint32_t c = carry_s;
+    if (i < ntiles) tile_sums[i] = off + c;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = c + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry_s;
+}
+// offsets[i] += tile_sums[tile(i)]; also seeds the scatter cursors and writes offsets[n] = grand total
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors, size_t n, const uint32_t* __restrict__ tile_sums,
+                                                    const uint32_t* __restrict__ grand_total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i <= n; i += (size_t)gridDim.x * blockDim.x) {
+    if (i == n) { offsets[n] = *grand_total; continue; }
+    uint32_t o = offsets[i] + tile_sums[i / SCAN_TILE];
+    offsets[i] = o; cursors[i] = o;
+  }
+}
+
+// S lanes per key; lanes of one key are adjacent, partials are combined with warp shuffles
+__device__ __forceinline__ G1XYZZ shfl_down_xyzz(const G1XYZZ& p, int off) {
+  G1XYZZ r;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], off);
+    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], off);
+    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], off);
+    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], off);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(G1_THREADS) k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+                                                               const G1Affine* __restrict__ table, G1XYZZ* __restrict__ buckets, size_t nkeys, int S) {
+  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t key = tid / S; int s = (int)(tid % S);
+  G1XYZZ acc = xyzz_inf();
+  if (key < nkeys) {
+    uint32_t begin = offsets[key], end = offsets[key + 1];
+    for (uint32_t e = begin + s; e < end; e += S) {
+      uint32_t ent = entries[e];
+      G1Affine b = table[ent & 0x7fffffffu];
+      xyzz_madd(acc, b, (ent >> 31) != 0);
+    }
+  }
+  for (int off = S >> 1; off > 0; off >>= 1) {          // whole warp participates (grid is padded to full warps)
+    G1XYZZ o = shfl_down_xyzz(acc, off);
+    if (s < off) acc = xyzz_add(acc, o);
+  }
+  if (key < nkeys && s == 0) buckets[key] = acc;
+}
+
+// one CTA per window group: R = sum_{k=1..K} k * B_k
+__global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, G1XYZZ* __restrict__ group_out) {
+  G1XYZZ* sm = reinterpret_cast<G1XYZZ*>(g1_dyn_smem);
+  const G1XYZZ* B = buckets + (size_t)blockIdx.x * K;
+  int T = blockDim.x;
+  int L = K >= T ? K / T : 1;                                 // K and T are powers of two
+  int lo = threadIdx.x * L;
+  G1XYZZ val = xyzz_inf();
+  if (lo < K) {
+    G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
+    for (int b = lo + L - 1; b >= lo; --b) { run = xyzz_add(run, B[b]); tot = xyzz_add(tot, run); }
+    val = lo ? xyzz_add(tot, xyzz_mul_small(run, (uint32_t)lo)) : tot;
+  }
+  G1XYZZ r = block_sum_xyzz(val, sm);
+  if (threadIdx.x == 0) group_out[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int c, G1Jac* __restrict__ out) {
+  size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (row >= m) return;
+  G1XYZZ acc = groups[row * NG + NG - 1];
+  for (int w = NG - 2; w >= 0; --w) {
+    for (int d = 0; d < c; ++d) acc = xyzz_dbl(acc);
+    acc = xyzz_add(acc, groups[row * NG + w]);
+  }
+  out[row] = xyzz_to_jac(acc);
+}
+
+// ------------------------------------------------------------------------------------------------ me_open scalars
+// Single CTA.  rows[(3j + {0,1,2}) * n + I] = scalars of T, T0, T1 of round j over the ORIGINAL generators;
+// rows[3k * n + I] = weights of the final folded generator; ret = final folded scalar.  See DESIGN.md §Opening.
+__global__ void __launch_bounds__(512) k_open_scalars(const Fr* __restrict__ s0, const Fr* __restrict__ u, int k, size_t n, Fr* __restrict__ rows,
+                                                      Fr* sA, Fr* sB, Fr* wA, Fr* wB, Fr* __restrict__ ret) {
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) sA[i] = s0[i];
+  if (threadIdx.x == 0) wA[0] = Fr::one();
+  __syncthreads();
+  Fr *s = sA, *sn = sB, *w = wA, *wn = wB;
+  for (int j = 0; j < k; ++j) {
+    size_t B = (size_t)1 << j, nj = n >> j;
+    Fr* T = rows + (size_t)(3 * j) * n; Fr* T0 = T + n; Fr* T1 = T0 + n;
+    for (size_t I = threadIdx.x; I < n; I += blockDim.x) {
+      size_t i = I >> j, b = I & (B - 1);
+      Fr wb = w[b];
+      T[I] = mul(s[i], wb);                       // raw Montgomery limbs of s times Montgomery weight = plain integer
+      if (i & 1) { T0[I] = mul(s[i - 1], wb); T1[I] = Fr::zero(); }
+      else { T1[I] = mul(s[i + 1], wb); T0[I] = Fr::zero(); }
+    }
+    Fr uj = u[j];
+    for (size_t g = threadIdx.x; g < nj / 2; g += blockDim.x) sn[g] = add(s[2 * g], mul(uj, sub(s[2 * g + 1], s[2 * g])));   // commitment.cu:55
+    for (size_t b = threadIdx.x; b < B; b += blockDim.x) {    // G' = [u'] G0 + [1-u'] G1  (commitment.cu:56)
+      Fr wb = w[b], hi = mul(wb, uj);
+      wn[b] = hi; wn[B + b] = sub(wb, hi);
+    }
+    __syncthreads();
+    Fr* t = s; s = sn; sn = t; t = w; w = wn; wn = t;
+  }
+  Fr* last = rows + (size_t)(3 * k) * n;
+  for (size_t I = threadIdx.x; I < n; I += blockDim.x) last[I] = from_mont(w[I]);
+  if (threadIdx.x == 0) ret[0] = s[0];
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+struct zkdl_g1_table {
+  size_t n; int full; int windows;
+  G1Affine* pts; size_t bytes;
+};
+
+namespace zk {
+
+static int pick_c(const zkdl_g1_table* t, size_t m) {
+  if (t->full) return m >= 64 ? 8 : 12;
+  int lg = 0; while (((size_t)1 << (lg + 1)) <= t->n) ++lg;
+  int c = lg - 5; if (c < 4) c = 4; if (c > 16) c = 16;
+  return c;
+}
+
+int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c_override, G1Jac* out, cudaStream_t st) {
+  if (m == 0) return ZK_OK;
+  MsmCfg cfg;
+  cfg.n = t->n; cfg.m = m; cfg.full = t->full; cfg.mont = mont;
+  cfg.c = c_override ? c_override : pick_c(t, m);
+  if (cfg.full) { cfg.c = (cfg.c / TABLE_C) * TABLE_C; if (cfg.c < TABLE_C) cfg.c = TABLE_C; if (cfg.c > 16) cfg.c = 16; }
+  cfg.tstep = cfg.c / TABLE_C;
+  cfg.W = (255 + cfg.c - 1) / cfg.c;
+  cfg.K = 1 << (cfg.c - 1);
+  cfg.NG = cfg.full ? 1 : cfg.W;
+  size_t nkeys = m * (size_t)cfg.NG * cfg.K;
+  size_t max_entries = m * cfg.n * (size_t)cfg.W;
+  ZK_REQUIRE(max_entries < 0xffffffffull && nkeys < 0x7fffffffull, ZK_ERR_ARG, "MSM too large for 32-bit entry indices");
+  ZK_REQUIRE(!cfg.full || (size_t)cfg.W * cfg.tstep * cfg.n < 0x80000000ull, ZK_ERR_ARG, "table too large");
+  // lanes per bucket: enough threads for ~4 waves of 148 SMs x 512 threads, at most 32
+  size_t want = (size_t)num_sms() * 512 * 2;
+  int Sl = 1; while (Sl < 32 && nkeys * Sl < want && (max_entries / (nkeys * Sl)) >= 8) Sl <<= 1;
+  cfg.S = Sl;
+
+  Scratch counts, offsets, cursors, tiles, total, entries, buckets, groups; int rc;
+  unsigned ntiles = div_up(nkeys, SCAN_TILE);
+  if ((rc = counts.alloc(sizeof(uint32_t) * nkeys, st))) return rc;
+  if ((rc = offsets.alloc(sizeof(uint32_t) * (nkeys + 1), st))) return rc;
+  if ((rc = cursors.alloc(sizeof(uint32_t) * nkeys, st))) return rc;
+  if ((rc = tiles.alloc(sizeof(uint32_t) * ntiles, st))) return rc;
+  if ((rc = total.alloc(sizeof(uint32_t), st))) return rc;
+  if ((rc = entries.alloc(sizeof(uint32_t) * max_entries, st))) return rc;
+  if ((rc = buckets.alloc(sizeof(G1XYZZ) * nkeys, st))) return rc;
+  if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG, st))) return rc;
+
+  ZK_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * nkeys, st));
+  unsigned dgrid = g1_grid(m * cfg.n, 256);
+  ZK_LAUNCH(k_msm_digits<false><<<dgrid, 256, 0, st>>>(scalars, cfg, counts.as<uint32_t>(), nullptr));
+  ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), nkeys, tiles.as<uint32_t>()));
+  ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(tiles.as<uint32_t>(), ntiles, total.as<uint32_t>()));
+  ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(offsets.as<uint32_t>(), cursors.as<uint32_t>(), nkeys, tiles.as<uint32_t>(), total.as<uint32_t>()));
+  ZK_LAUNCH(k_msm_digits<true><<<dgrid, 256, 0, st>>>(scalars, cfg, cursors.as<uint32_t>(), entries.as<uint32_t>()));
+  size_t athreads = nkeys * cfg.S;
+  ZK_LAUNCH(k_msm_accumulate<<<div_up(athreads, G1_THREADS), G1_THREADS, 0, st>>>(entries.as<uint32_t>(), offsets.as<uint32_t>(), t->pts,
+                                                                                   buckets.as<G1XYZZ>(), nkeys, cfg.S));
+  int T = cfg.K < 32 ? 32 : (cfg.K > 256 ? 256 : cfg.K);
+  ZK_LAUNCH(k_msm_reduce<<<(unsigned)(m * cfg.NG), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>()));
+  ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, cfg.c, out));
+  return ZK_OK;
+}
+
+static int me_open_run(const zkdl_g1_table* gens, const Fr* t, size_t n, const zkdl_fr_t* u_host, size_t k, G1Jac* proof, Fr* ret, cudaStream_t st) {
+  ZK_REQUIRE(n == gens->n, ZK_ERR_DIM, "Incompatible dimensions");                       // commitment.cu:64
+  ZK_REQUIRE(k < 31 && n == ((size_t)1 << k), ZK_ERR_DIM, "Incompatible dimensions");    // even halving at every round (commitment.cu:46)
+  Scratch ud, rows, sA, sB, wA, wB; int rc;
+  if ((rc = ud.alloc(sizeof(Fr) * (k ? k : 1), st))) return rc;
+  if (k) ZK_CUDA(cudaMemcpyAsync(ud.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  if ((rc = rows.alloc(sizeof(Fr) * (3 * k + 1) * n, st))) return rc;
+  if ((rc = sA.alloc(sizeof(Fr) * n, st))) return rc;
+  if ((rc = sB.alloc(sizeof(Fr) * n, st))) return rc;
+  if ((rc = wA.alloc(sizeof(Fr) * n, st))) return rc;
+  if ((rc = wB.alloc(sizeof(Fr) * n, st))) return rc;
+  ZK_LAUNCH(k_open_scalars<<<1, 512, 0, st>>>(t, ud.as<Fr>(), (int)k, n, rows.as<Fr>(), sA.as<Fr>(), sB.as<Fr>(), wA.as<Fr>(), wB.as<Fr>(), ret));
+  return msm_run(gens, rows.as<Fr>(), 3 * k + 1, 0, 0, proof, st);
+}
+
+int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr* t, size_t nt, const zkdl_fr_t* u_host, size_t ku,
+             G1Jac* com_eval, G1Jac* proof, Fr* ret, cudaStream_t st) {
+  size_t ncom = com_table->n;
+  size_t khi = zkdl_ceil_log2((uint32_t)ncom);
+  ZK_REQUIRE(ku >= khi, ZK_ERR_DIM, "Incompatible dimensions");
+  size_t klo = ku - khi;
+  const zkdl_fr_t* u_hi = u_host + klo;
+  ZK_REQUIRE(klo < 31 && gens->n == ((size_t)1 << klo), ZK_ERR_DIM, "Incompatible dimensions");   // commitment.cu:89
+  // com(u_hi): G1_me == MSM of com against eq(u_hi, .) (g1-tensor.cu:463-491); guard of G1TensorJacobian::operator()(u)
+  if (khi > 0) ZK_REQUIRE(!(ncom <= ((size_t)1 << (khi - 1)) || ncom > ((size_t)1 << khi)), ZK_ERR_DIM, "Incompatible dimensions");
+  Scratch uq, E, tf; int rc;
+  if ((rc = uq.alloc(sizeof(Fr) * (khi ? khi : 1), st))) return rc;
+  if (khi) ZK_CUDA(cudaMemcpyAsync(uq.p, u_hi, sizeof(Fr) * khi, cudaMemcpyHostToDevice, st));
+  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << khi), st))) return rc;
+  if ((rc = build_eq_table(uq.as<Fr>(), u_hi, (int)khi, 0, E.as<Fr>(), st))) return rc;
+  if ((rc = msm_run(com_table, E.as<Fr>(), 1, 1, 0, com_eval, st))) return rc;
+  // t.partial_me(u_hi, |gens|)
+  size_t w = gens->n;
+  if (khi > 0) ZK_REQUIRE(nt > w * ((size_t)1 << (khi - 1)), ZK_ERR_DIM, "Incompatible dimensions");   // fr-tensor.cu:372
+  size_t tf_n = zkdl_partial_me_size(nt, khi, w);
+  ZK_REQUIRE(tf_n == w, ZK_ERR_DIM, "Incompatible dimensions");                                         // commitment.cu:64
+  if ((rc = tf.alloc(sizeof(Fr) * tf_n, st))) return rc;
+  if ((rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st))) return rc;
+  return me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zkdl_g1_elementwise(int op, const zkdl_g1_jacobian_t* a, const void* b, size_t nb, zkdl_g1_jacobian_t* out, size_t n, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_REQUIRE(op >= ZKDL_G1_ADD && op <= ZKDL_G1_MSUB, ZK_ERR_ARG, "bad op");
+  if (op != ZKDL_G1_NEG) ZK_REQUIRE(b && (nb == 1 || nb == n), ZK_ERR_DIM, "Incompatible dimensions");
+  ZK_LAUNCH(k_g1_elementwise<<<g1_grid(n, G1_THREADS), G1_THREADS, 0, S(stream)>>>(op, reinterpret_cast<const G1Jac*>(a), b, nb, reinterpret_cast<G1Jac*>(out), n));
+  return ZK_OK;
+}
+int zkdl_g1_affine_to_jacobian(const zkdl_g1_affine_t* a, zkdl_g1_jacobian_t* out, size_t n, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_LAUNCH(k_g1_affine_to_jac<<<g1_grid(n, G1_THREADS), G1_THREADS, 0, S(stream)>>>(reinterpret_cast<const G1Affine*>(a), reinterpret_cast<G1Jac*>(out), n));
+  return ZK_OK;
+}
+int zkdl_g1_mul(const zkdl_g1_jacobian_t* P, size_t np, const zkdl_fr_t* x, size_t n, zkdl_g1_jacobian_t* out, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_REQUIRE(np > 0 && n % np == 0, ZK_ERR_DIM, "Incompatible dimensions");                // g1-tensor.cu:448
+  ZK_LAUNCH(k_g1_mul<<<g1_grid(n, G1_THREADS), G1_THREADS, 0, S(stream)>>>(reinterpret_cast<const G1Jac*>(P), np, reinterpret_cast<const Fr*>(x), n, reinterpret_cast<G1Jac*>(out)));
+  return ZK_OK;
+}
+int zkdl_g1_sum(const zkdl_g1_jacobian_t* a, size_t n, zkdl_g1_jacobian_t* out, void* stream) {
+  cudaStream_t st = S(stream);
+  unsigned grid = g1_grid(n, G1_THREADS); if (grid > 1024) grid = 1024;
+  Scratch parts; int rc = parts.alloc(sizeof(G1XYZZ) * grid, st); if (rc) return rc;
+  ZK_LAUNCH(k_g1_sum_partial<<<grid, G1_THREADS, sizeof(G1XYZZ) * G1_THREADS, st>>>(reinterpret_cast<const G1Jac*>(a), n, parts.as<G1XYZZ>()));
+  ZK_LAUNCH(k_g1_sum_final<<<1, G1_THREADS, sizeof(G1XYZZ) * G1_THREADS, st>>>(parts.as<G1XYZZ>(), grid, reinterpret_cast<G1Jac*>(out)));
+  return ZK_OK;
+}
+int zkdl_g1_normalize(const zkdl_g1_jacobian_t* a, zkdl_g1_jacobian_t* out, size_t n, void* stream) {
+  if (n == 0) return ZK_OK;
+  ZK_LAUNCH(k_g1_normalize<<<g1_grid(n, G1_THREADS), G1_THREADS, 0, S(stream)>>>(reinterpret_cast<const G1Jac*>(a), reinterpret_cast<G1Jac*>(out), n));
+  return ZK_OK;
+}
+
+int zkdl_g1_table_create(const zkdl_g1_jacobian_t* points, size_t n, int window_bits, int full, zkdl_g1_table** out, void* stream) {
+  cudaStream_t st = S(stream);
+  ZK_REQUIRE(points && out && n > 0, ZK_ERR_ARG, "bad table arguments");
+  ZK_REQUIRE(window_bits == 0 || window_bits == TABLE_C, ZK_ERR_ARG, "only 4-bit table windows are supported");
+  int windows = full ? TABLE_W : 1;
+  size_t total = n * (size_t)windows;
+  zkdl_g1_table* t = new zkdl_g1_table();
+  t->n = n; t->full = full; t->windows = windows; t->bytes = total * sizeof(G1Affine); t->pts = nullptr;
+  cudaError_t e = cudaMalloc(&t->pts, t->bytes);
+  if (e != cudaSuccess) { delete t; set_last_error("cudaMalloc table: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  Scratch tmp; int rc = tmp.alloc(sizeof(G1XYZZ) * total, st);
+  if (rc) { cudaFree(t->pts); delete t; return rc; }
+  k_table_expand<<<div_up(n, G1_THREADS), G1_THREADS, 0, st>>>(reinterpret_cast<const G1Jac*>(points), n, windows, tmp.as<G1XYZZ>());
+  k_batch_affine<<<div_up(div_up(total, INV_CH), G1_THREADS), G1_THREADS, 0, st>>>(tmp.as<G1XYZZ>(), t->pts, total);
+  zk::g_launches.fetch_add(2);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(t->pts); delete t; set_last_error("table kernels: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  *out = t;
+  return ZK_OK;
+}
+int zkdl_g1_table_destroy(zkdl_g1_table* t) {
+  if (!t) return ZK_OK;
+  cudaFree(t->pts);
+  delete t;
+  return ZK_OK;
+}
+size_t zkdl_g1_table_size(const zkdl_g1_table* t) { return t ? t->n : 0; }
+size_t zkdl_g1_table_bytes(const zkdl_g1_table* t) { return t ? t->bytes : 0; }
+
+int zkdl_msm(const zkdl_g1_table* t, const zkdl_fr_t* scalars, size_t m, int scalars_mont, zkdl_g1_jacobian_t* out, void* stream) {
+  ZK_REQUIRE(t && scalars && out, ZK_ERR_ARG, "null argument");
+  return msm_run(t, reinterpret_cast<const Fr*>(scalars), m, scalars_mont, 0, reinterpret_cast<G1Jac*>(out), S(stream));
+}
+int zkdl_commit(const zkdl_g1_table* gens, const zkdl_fr_t* t, size_t nt, zkdl_g1_jacobian_t* com, void* stream) {
+  ZK_REQUIRE(gens && t && com, ZK_ERR_ARG, "null argument");
+  ZK_REQUIRE(nt % gens->n == 0, ZK_ERR_DIM, "Incompatible dimensions");                    // commitment.cu:31
+  return msm_run(gens, reinterpret_cast<const Fr*>(t), nt / gens->n, 1, 0, reinterpret_cast<G1Jac*>(com), S(stream));
+}
+int zkdl_me_open(const zkdl_g1_table* gens, const zkdl_fr_t* t, size_t n, const zkdl_fr_t* u_host, size_t k,
+                 zkdl_g1_jacobian_t* proof, zkdl_fr_t* ret, void* stream) {
+  ZK_REQUIRE(gens && t && proof && ret, ZK_ERR_ARG, "null argument");
+  return me_open_run(gens, reinterpret_cast<const Fr*>(t), n, u_host, k, reinterpret_cast<G1Jac*>(proof), reinterpret_cast<Fr*>(ret), S(stream));
+}
+int zkdl_open(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const zkdl_fr_t* t, size_t nt, const zkdl_fr_t* u_host, size_t ku,
+              zkdl_g1_jacobian_t* com_eval, zkdl_g1_jacobian_t* proof, zkdl_fr_t* ret, void* stream) {
+  ZK_REQUIRE(gens && com_table && t && com_eval && proof && ret, ZK_ERR_ARG, "null argument");
+  return open_run(gens, com_table, reinterpret_cast<const Fr*>(t), nt, u_host, ku, reinterpret_cast<G1Jac*>(com_eval),
+                  reinterpret_cast<G1Jac*>(proof), reinterpret_cast<Fr*>(ret), S(stream));
+}
+int zkdl_g1_me(const zkdl_g1_jacobian_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, zkdl_g1_jacobian_t* out, void* stream) {
+  cudaStream_t st = S(stream);
+  ZK_REQUIRE(k < 31, ZK_ERR_DIM, "Incompatible dimensions");
+  if (k == 0) { ZK_REQUIRE(n == 1, ZK_ERR_DIM, "Incompatible dimensions"); ZK_CUDA(cudaMemcpyAsync(out, a, sizeof(G1Jac), cudaMemcpyDeviceToDevice, st)); return ZK_OK; }
+  ZK_REQUIRE(!(n <= ((size_t)1 << (k - 1)) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");   // g1-tensor.cu:488
+  zkdl_g1_table* tab = nullptr;
+  int rc = zkdl_g1_table_create(a, n, 0, 0, &tab, stream); if (rc) return rc;
+  Scratch uq, E;
+  if ((rc = uq.alloc(sizeof(Fr) * k, st))) { zkdl_g1_table_destroy(tab); return rc; }
+  cudaMemcpyAsync(uq.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st);
+  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << k), st))) { zkdl_g1_table_destroy(tab); return rc; }
+  rc = build_eq_table(uq.as<Fr>(), u_host, (int)k, 0, E.as<Fr>(), st);
+  if (!rc) rc = msm_run(tab, E.as<Fr>(), 1, 1, 0, reinterpret_cast<G1Jac*>(out), st);
+  cudaStreamSynchronize(st);                     // the temporary table must outlive the kernels
+  zkdl_g1_table_destroy(tab);
+  return rc;
+}
+
+}  // extern "C"
