@@ -136,7 +136,7 @@ def fr_me(a, u):
 
 def fr_partial_me(a, u, window):
     a, u = _c(a, 8), _c(np.asarray(u).reshape(-1, 8), 8)
-    out = np.zeros((max(len(a), 1), 8), np.uint32)
+    out = np.zeros((len(a) + 2 * int(window) + 1, 8), np.uint32)
     n = lib().orc_fr_partial_me(_p(a), _sz(len(a)), _p(u), _sz(len(u)), _sz(window), _p(out))
     return out[:n].copy()
 

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_fold_tail(Fr* a0, Fr* a1, cons
     Fr* t = a; a = an; an = t;
     in_size = out_size;
   }
-  if (threadIdx.x == 0) out[0] = a[0];
+  for (size_t g = threadIdx.x; g < in_size; g += blockDim.x) out[g] = a[g];     // whatever is left of the table
 }
 
 // ------------------------------------------------------------------------------------------------ quantise / matmul / relu
@@ -323,9 +323,7 @@ static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k,
   while (j < k) {
     size_t left = k - j;
     if (w == 1 && cur_n <= TAIL_N && cur != a) {        // finish in one CTA (needs a writable current buffer)
-      Scratch res; if ((rc = res.alloc(sizeof(Fr), st))) return rc;
-      ZK_LAUNCH(k_fold_tail<<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(cur), bufs[which], xs.as<Fr>() + j, (int)left, cur_n, res.as<Fr>()));
-      ZK_CUDA(cudaMemcpyAsync(out, res.p, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+      ZK_LAUNCH(k_fold_tail<<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(cur), bufs[which], xs.as<Fr>() + j, (int)left, cur_n, out));
       return ZK_OK;
     }
     int R = left >= 3 ? 3 : (left == 2 ? 2 : 1);

@@ -1,0 +1,119 @@
+"""Host-side driver of the demo path (mirrors /root/reference/demo.cu:23-143 over the C ABI): load float weights,
+build generators, commit, quantised forward pass, then the backward proving loop zkFC::prove / zkReLU::prove.
+
+Python mirror of zkdl_b200/host/demo.cpp, used by bench.py and the tests.  Randomness is injected: generators and
+challenges come from seeded streams (the reference uses std::random_device)."""
+import numpy as np
+
+from . import capi as zk
+
+
+def ceil_log2(n):
+    return 0 if n <= 1 else (int(n) - 1).bit_length()
+
+
+def pad2(n):
+    return 1 << ceil_log2(n)
+
+
+def demo_layer_dims():
+    """model.py:14-30 — the 18.2 M-parameter ModulusLab benchmark MLP."""
+    d = [784, 1000, 1773, 1773, 1773, 1773, 1773, 1124, 1000]
+    return list(zip(d[:-1], d[1:]))
+
+
+class Layer:
+    pass
+
+
+class MLPProver:
+    """weights: list of float32 CUDA tensors shaped [in, out] (== nn.Linear.weight.t(), demo.cu:72)."""
+
+    def __init__(self, weights, gen_seed=1):
+        import torch
+        self.layers = []
+        rng = np.random.default_rng(gen_seed)
+        gen = zk.to_device(_generator())
+        for w in weights:
+            L = Layer()
+            L.in_dim, L.out_dim = int(w.shape[0]), int(w.shape[1])
+            L.I, L.O = pad2(L.in_dim), pad2(L.out_dim)
+            L.ngens = 1 << ((ceil_log2(L.in_dim * L.out_dim) + 1) // 2)                      # demo.cu:81
+            ks = rng.integers(0, 1 << 32, size=(L.ngens, 8), dtype=np.uint64).astype(np.uint32)
+            ks[:, 7] %= 1944954707                                                           # fr-tensor.cu:346
+            L.G = zk.g1_mul(gen, zk.to_device(ks))                                           # generators *= random (demo.cu:82)
+            L.gens = zk.G1Table(L.G, full=True)
+            q = zk.float_to_fr(w.contiguous(), L.I, L.O)                                     # zkfc.cu:90-100
+            L.W = zk.fr_elementwise(zk.OP_MONT, q, out=q)
+            L.com = zk.commit(L.gens, L.W)                                                   # zkfc.cu:102
+            L.com_table = zk.G1Table(L.com, full=True)
+            self.layers.append(L)
+        self.n_params = sum(L.in_dim * L.out_dim for L in self.layers)
+        torch.cuda.synchronize()
+
+    def forward(self, x):
+        """x: float32 CUDA [batch, in].  Keeps Z_i, A_i and the ReLU aux tables (demo.cu:23-38)."""
+        B = pad2(x.shape[0])
+        L0 = self.layers[0]
+        X = zk.float_to_fr(x.contiguous(), B, L0.I)                                          # zkfc.cu:106-115
+        self.X = zk.fr_elementwise(zk.OP_MONT, X, out=X)                                     # demo.cu:119
+        self.B = B
+        self.Z, self.A, self.aux = [], [], []
+        cur = self.X
+        for i, L in enumerate(self.layers):
+            z = zk.fr_matmul(cur, L.W, B, L.I, L.O)
+            self.Z.append(z)
+            if i + 1 < len(self.layers):
+                a, sign, mag, rem, bad = zk.relu(z)
+                self.A.append(a); self.aux.append((sign, mag, rem))
+                cur = a
+        return self.Z[-1]
+
+    def prove(self, seed=0):
+        """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order."""
+        ctr = [seed]
+
+        def rv(k):
+            ctr[0] += 1
+            return zk.random_vec(ctr[0], k)
+
+        B, kb = self.B, ceil_log2(self.B)
+        out = []
+        nl = len(self.layers)
+
+        def fc(i):
+            L = self.layers[i]
+            Xin = self.A[i - 1] if i > 0 else self.X
+            u_bs, u_in, u_out = rv(kb), rv(ceil_log2(L.I)), rv(ceil_log2(L.O))               # zkfc.cu:135-137
+            out.append(("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, u_bs, u_in, u_out))
+
+        def relu(i):
+            n = B * self.layers[i].O
+            Lg = ceil_log2(n)
+            ch = [rv(Lg + 5), rv(Lg + 5), rv(Lg + 4), rv(Lg + 4), rv(Lg)]                    # zkrelu.cu:85-89
+            ch += [rv(Lg), rv(Lg)]                                                           # zkrelu.cu:97-98
+            sign, mag, rem = self.aux[i]
+            out.append(("relu", i, zk.zkrelu_prove(self.Z[i], sign, mag, rem, *ch)))
+
+        fc(nl - 1)
+        for i in range(nl - 2, -1, -1):
+            relu(i)
+            fc(i)
+        return out
+
+
+def _generator():
+    """G1Jacobian_generator (g1-tensor.cuh:28-63)."""
+    gx = [4250078230, 1555269520, 2574712821, 2014837863, 339452353, 357537223, 4090554183, 4037962445, 568063040, 3989728972, 2651585397, 302085953]
+    gy = [216474225, 3131872213, 2031680910, 2351063834, 1460086222, 3713621779, 1346392468, 1370249257, 2902481344, 236751935, 1342743146, 196886268]
+    one = [196605, 1980301312, 3289120770, 3958636555, 1405573306, 1598593111, 1884444485, 2010011731, 2723605613, 1543969431, 4202751123, 368467651]
+    return np.array([gx + gy + one], dtype=np.uint32)
+
+
+def synthetic_mlp(dims, batch, seed=0, device="cuda"):
+    """PyTorch-default U(-1/sqrt(in), 1/sqrt(in)) weights and N(0,1) inputs of the named shapes (model.py)."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    ws = [((torch.rand(i, o, generator=g) * 2 - 1) / (i ** 0.5)).float().to(device) for i, o in dims]
+    x = torch.randn(batch, dims[0][0], generator=g).float().to(device)
+    return ws, x
