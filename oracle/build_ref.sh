@@ -7,6 +7,7 @@
 #                            challenges/generators through the reference's public API and dumps every result
 # The reference has no CPU path, so these binaries only run on the GPU box.
 set -e
+set -o pipefail
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
 OUT=$HERE/_ref

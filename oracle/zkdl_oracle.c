@@ -104,6 +104,7 @@ void orc_fr_sum(const ofr_t* a, size_t n, ofr_t* out) {                         
 
 /* fold(T,x)[g] = T[2g] + x (T[2g+1] - T[2g]); missing entries are 0 (fr-tensor.cu:399-409) */
 static void fr_me_step(const ofr_t* in, ofr_t* out, const ofr_t* x, size_t in_size, size_t out_size) {
+#pragma omp parallel for schedule(static) if (out_size > 4096)
   for (size_t g = 0; g < out_size; ++g) {
     size_t g0 = 2 * g, g1 = 2 * g + 1; ofr_t t;
     if (g1 < in_size) { fr_sub(&t, in + g1, in + g0); fr_mul(&t, x, &t); fr_add(out + g, in + g0, &t); }
@@ -131,6 +132,7 @@ size_t orc_fr_partial_me(const ofr_t* a, size_t n, const ofr_t* u, size_t k, siz
   for (size_t j = 0; j < k; ++j) {
     size_t nw = (sz + 2 * w - 1) / (2 * w), o = w * nw;
     ofr_t* nx = (ofr_t*)malloc(sizeof(ofr_t) * (o ? o : 1));
+#pragma omp parallel for schedule(static) if (o > 4096)
     for (size_t g = 0; g < o; ++g) {
       size_t wid = g / w, idx = g % w, g0 = 2 * wid * w + idx, g1 = (2 * wid + 1) * w + idx; ofr_t t;
       if (g1 < sz) { fr_sub(&t, cur + g1, cur + g0); fr_mul(&t, u + j, &t); fr_add(nx + g, cur + g0, &t); }
@@ -146,6 +148,7 @@ size_t orc_fr_partial_me(const ofr_t* a, size_t n, const ofr_t* u, size_t k, siz
 
 /* per-pair coefficient vectors (proof.cu:55-70) */
 static void ip_step(const ofr_t* a, const ofr_t* b, ofr_t* o0, ofr_t* o1, ofr_t* o2, size_t in_size, size_t out_size) {
+#pragma omp parallel for schedule(static) if (out_size > 4096)
   for (size_t g = 0; g < out_size; ++g) {
     size_t g0 = 2 * g, g1 = 2 * g + 1;
     ofr_t a0 = g0 < in_size ? a[g0] : FR_ZERO_C, b0 = g0 < in_size ? b[g0] : FR_ZERO_C;
@@ -158,6 +161,7 @@ static void ip_step(const ofr_t* a, const ofr_t* b, ofr_t* o0, ofr_t* o1, ofr_t*
   }
 }
 static void bin_step(const ofr_t* a, ofr_t* o0, ofr_t* o1, ofr_t* o2, size_t in_size, size_t out_size) { /* proof.cu:152-163 */
+#pragma omp parallel for schedule(static) if (out_size > 4096)
   for (size_t g = 0; g < out_size; ++g) {
     ofr_t a0 = 2 * g < in_size ? a[2 * g] : FR_ZERO_C, a1 = 2 * g + 1 < in_size ? a[2 * g + 1] : FR_ZERO_C;
     ofr_t t, d, d2;

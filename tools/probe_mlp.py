@@ -21,7 +21,9 @@ def timed(fn, name, reps=3):
         print(f"{name}: {e0.elapsed_time(e1):.3f} ms device, {1e3*(time.time()-t0):.3f} ms wall, {zk.launch_count()-l0} launches")
     return out
 timed(lambda: P.forward(x), "forward")
-proof = timed(lambda: P.prove(seed=100), "prove", reps=4)
+proof = timed(lambda: P.prove(seed=100, streams=1), "prove 1 stream", reps=3)
+for ns in (2, 4, 8, 15):
+    timed(lambda: P.prove(seed=100, streams=ns), f"prove {ns} streams", reps=3)
 # per-call breakdown of one layer
 L = P.layers[2]; B = P.B
 import numpy as np

@@ -56,7 +56,18 @@ inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)(
 #endif
 
 // ---------------------------------------------------------------- field parameters
+// Montgomery products are emitted as real calls (not inlined) where a kernel chains many of them: a G1 mixed add is
+// 10 Fq products = ~60 KB of straight-line SASS when inlined, far beyond the 32 KB L1.5 instruction cache, and the
+// first profile showed the MSM kernels instruction-fetch bound (profiles/r1_v1_layer_launches.csv).  Arguments travel
+// in registers (by value), so a call costs ~36 MOVs against ~370 arithmetic instructions.
+#ifndef ZK_FR_OUTLINE_MUL
+#define ZK_FR_OUTLINE_MUL 0
+#endif
+#ifndef ZK_FQ_OUTLINE_MUL
+#define ZK_FQ_OUTLINE_MUL 1
+#endif
 struct FrParams {
+  static constexpr bool OUTLINE_MUL = ZK_FR_OUTLINE_MUL != 0;
   static constexpr int N = 8;
   static constexpr uint32_t INV = 0xffffffffu;               // -p^-1 mod 2^32  (bls12-381.cuh:119)
   ZK_HD static uint32_t P(int i) {
@@ -73,6 +84,7 @@ struct FrParams {
   }
 };
 struct FqParams {
+  static constexpr bool OUTLINE_MUL = ZK_FQ_OUTLINE_MUL != 0;
   static constexpr int N = 12;
   static constexpr uint32_t INV = 0xfffcfffdu;               // bls12-381.cuh:221
   ZK_HD static uint32_t P(int i) {
@@ -200,7 +212,7 @@ ZK_HD void mont_row(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi) 
 }
 
 template <class PR>
-ZK_HD Fe<PR> mul(const Fe<PR>& a, const Fe<PR>& b) {        // Scalar_mul / Fp_mul (bls12-381.cu:462-494, 869-901)
+ZK_HD Fe<PR> mul_impl(const Fe<PR>& a, const Fe<PR>& b) {   // Scalar_mul / Fp_mul (bls12-381.cu:462-494, 869-901)
   constexpr int N = PR::N;
   uint32_t ev[N], od[N];
   mont_row<PR, true>(ev, od, a.v, b.v[0]);
@@ -218,6 +230,17 @@ ZK_HD Fe<PR> mul(const Fe<PR>& a, const Fe<PR>& b) {        // Scalar_mul / Fp_m
   return r;
 }
 
+#if defined(__CUDA_ARCH__)
+template <class PR>
+__device__ __noinline__ Fe<PR> mul_outlined(Fe<PR> a, Fe<PR> b) { return mul_impl(a, b); }
+#endif
+template <class PR>
+ZK_HD Fe<PR> mul(const Fe<PR>& a, const Fe<PR>& b) {
+#if defined(__CUDA_ARCH__)
+  if (PR::OUTLINE_MUL) return mul_outlined<PR>(a, b);
+#endif
+  return mul_impl(a, b);
+}
 template <class PR>
 ZK_HD Fe<PR> sqr(const Fe<PR>& a) { return mul(a, a); }
 template <class PR>

@@ -164,7 +164,6 @@ struct MsmCfg {
   int NG;               // window groups per row: 1 with full tables, W otherwise
   int full, tstep;      // full tables; table windows per digit window (c / TABLE_C)
   int mont;             // scalars are Montgomery
-  int S;                // lanes per bucket in the accumulate kernel (power of two <= 32)
 };
 
 template <bool SCATTER>
@@ -252,47 +251,104 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* __restrict__ offse
   }
 }
 
-// S lanes per key; lanes of one key are adjacent, partials are combined with warp shuffles
-__device__ __forceinline__ G1XYZZ shfl_down_xyzz(const G1XYZZ& p, int off) {
+// ---- skew-robust bucket accumulation.  The sorted entry list is cut into chunks of CH consecutive entries, one per
+// thread, regardless of bucket boundaries, so every thread performs exactly CH mixed additions whatever the digit
+// distribution is (a 254-bit scalar leaves the top window with 2 bits of entropy: three buckets receive a third of
+// all points each).  A chunk that spans several buckets emits one partial per bucket; partial slot of (key, chunk t)
+// = P[key] + t - floor(offset[key] / CH), P = exclusive scan of the per-key chunk counts.
+// plan[0] = CH (entries per chunk), plan[1] = number of chunks; decided on the device from the real entry count so that
+// the host never synchronises: CH = max(4, ceil(total / target)) => at most target + 1 chunks.
+__global__ void k_msm_plan(const uint32_t* __restrict__ offsets, size_t nkeys, uint32_t target, uint32_t* __restrict__ plan) {
+  uint32_t total = offsets[nkeys];
+  uint32_t CH = (total + target - 1) / target; if (CH < 4) CH = 4;
+  plan[0] = CH; plan[1] = (total + CH - 1) / CH;
+}
+__global__ void __launch_bounds__(256) k_msm_chunk_counts(const uint32_t* __restrict__ offsets, size_t nkeys, const uint32_t* __restrict__ plan, uint32_t* __restrict__ counts) {
+  const uint32_t CH = plan[0];
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nkeys; k += (size_t)gridDim.x * blockDim.x) {
+    uint32_t b = offsets[k], e = offsets[k + 1];
+    counts[k] = b == e ? 0u : ((e - 1) / CH - b / CH + 1u);
+  }
+}
+__device__ __forceinline__ G1XYZZ shfl_xyzz(const G1XYZZ& p, int src_lane_delta_down) {
   G1XYZZ r;
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
-    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], off);
-    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], off);
-    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], off);
-    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], off);
+    r.x.v[i] = __shfl_down_sync(0xffffffffu, p.x.v[i], src_lane_delta_down);
+    r.y.v[i] = __shfl_down_sync(0xffffffffu, p.y.v[i], src_lane_delta_down);
+    r.zz.v[i] = __shfl_down_sync(0xffffffffu, p.zz.v[i], src_lane_delta_down);
+    r.zzz.v[i] = __shfl_down_sync(0xffffffffu, p.zzz.v[i], src_lane_delta_down);
   }
   return r;
 }
-__global__ void __launch_bounds__(G1_THREADS) k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
-                                                               const G1Affine* __restrict__ table, G1XYZZ* __restrict__ buckets, size_t nkeys, int S) {
-  size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  size_t key = tid / S; int s = (int)(tid % S);
+__global__ void __launch_bounds__(G1_THREADS, 3) k_msm_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+                                                                  const uint32_t* __restrict__ pslot, const G1Affine* __restrict__ table,
+                                                                  G1XYZZ* __restrict__ partials, size_t nkeys, const uint32_t* __restrict__ plan) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t CH = plan[0];
+  if (t >= plan[1]) return;
+  const uint32_t total = offsets[nkeys];
+  uint32_t a = t * CH, b = a + CH < total ? a + CH : total;
+  // key of entry a: largest k with offsets[k] <= a
+  size_t lo = 0, hi = nkeys;
+  while (hi - lo > 1) { size_t mid = (lo + hi) >> 1; if (offsets[mid] <= a) lo = mid; else hi = mid; }
+  size_t key = lo;
+  uint32_t key_end = offsets[key + 1];
   G1XYZZ acc = xyzz_inf();
-  if (key < nkeys) {
-    uint32_t begin = offsets[key], end = offsets[key + 1];
-    for (uint32_t e = begin + s; e < end; e += S) {
-      uint32_t ent = entries[e];
-      G1Affine b = table[ent & 0x7fffffffu];
-      xyzz_madd(acc, b, (ent >> 31) != 0);
+  for (uint32_t e = a; e < b; ++e) {
+    if (e >= key_end) {                                   // bucket boundary inside the chunk
+      partials[pslot[key] + (t - offsets[key] / CH)] = acc;
+      acc = xyzz_inf();
+      do { ++key; key_end = offsets[key + 1]; } while (e >= key_end);
     }
+    uint32_t ent = entries[e];
+    G1Affine base = table[ent & 0x7fffffffu];
+    xyzz_madd(acc, base, (ent >> 31) != 0);
   }
-  for (int off = S >> 1; off > 0; off >>= 1) {          // whole warp participates (grid is padded to full warps)
-    G1XYZZ o = shfl_down_xyzz(acc, off);
-    if (s < off) acc = xyzz_add(acc, o);
+  partials[pslot[key] + (t - offsets[key] / CH)] = acc;
+}
+// bucket[key] = sum of its partials.  Buckets with few partials: one lane each.  Buckets with many (the skewed ones)
+// are appended to a list and summed by one warp each in k_msm_combine_heavy (strided loads + shuffle tree).
+static constexpr uint32_t COMBINE_LIGHT = 6;
+__global__ void __launch_bounds__(G1_THREADS) k_msm_combine(const G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pslot, size_t nkeys,
+                                                            G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
+  size_t key = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (key >= nkeys) return;
+  uint32_t base = pslot[key], np = pslot[key + 1] - base;
+  if (np > COMBINE_LIGHT) { heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key; return; }
+  G1XYZZ acc = xyzz_inf();
+  for (uint32_t i = 0; i < np; ++i) acc = xyzz_add(acc, partials[base + i]);
+  buckets[key] = acc;
+}
+__global__ void __launch_bounds__(G1_THREADS) k_msm_combine_heavy(const G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pslot,
+                                                                  G1XYZZ* __restrict__ buckets, const uint32_t* __restrict__ heavy_list,
+                                                                  const uint32_t* __restrict__ heavy_count) {
+  size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= *heavy_count) return;                       // whole warp exits together
+  uint32_t key = heavy_list[warp];
+  uint32_t base = pslot[key], cnt = pslot[key + 1] - base;
+  G1XYZZ tmp = xyzz_inf();
+  for (uint32_t i = lane; i < cnt; i += 32) tmp = xyzz_add(tmp, partials[base + i]);
+  for (int off = 16; off > 0; off >>= 1) {
+    G1XYZZ o = shfl_xyzz(tmp, off);
+    if (lane < off) tmp = xyzz_add(tmp, o);
   }
-  if (key < nkeys && s == 0) buckets[key] = acc;
+  if (lane == 0) buckets[key] = tmp;
 }
 
-// one CTA per window group: R = sum_{k=1..K} k * B_k
-__global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, G1XYZZ* __restrict__ group_out) {
+// `split` CTAs per window group: CTA j reduces buckets [j*K/split, (j+1)*K/split) to sum_k k * B_k (global bucket
+// numbers) with per-thread running sums + a small-scalar offset + a shared-memory tree; k_msm_final adds the pieces.
+__global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, int split, G1XYZZ* __restrict__ group_out) {
   G1XYZZ* sm = reinterpret_cast<G1XYZZ*>(g1_dyn_smem);
-  const G1XYZZ* B = buckets + (size_t)blockIdx.x * K;
+  const int group = blockIdx.x / split, piece = blockIdx.x % split;
+  const int Kp = K / split;                                   // buckets in this piece
+  const G1XYZZ* B = buckets + (size_t)group * K;
   int T = blockDim.x;
-  int L = K >= T ? K / T : 1;                                 // K and T are powers of two
-  int lo = threadIdx.x * L;
+  int L = Kp >= T ? Kp / T : 1;                               // K, split and T are powers of two
+  int lo = piece * Kp + threadIdx.x * L;
   G1XYZZ val = xyzz_inf();
-  if (lo < K) {
+  if (threadIdx.x * L < Kp) {
     G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
     for (int b = lo + L - 1; b >= lo; --b) { run = xyzz_add(run, B[b]); tot = xyzz_add(tot, run); }
     val = lo ? xyzz_add(tot, xyzz_mul_small(run, (uint32_t)lo)) : tot;
@@ -300,13 +356,15 @@ __global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, G1XYZZ* 
   G1XYZZ r = block_sum_xyzz(val, sm);
   if (threadIdx.x == 0) group_out[blockIdx.x] = r;
 }
-__global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int c, G1Jac* __restrict__ out) {
+__global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int split, int c, G1Jac* __restrict__ out) {
   size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (row >= m) return;
-  G1XYZZ acc = groups[row * NG + NG - 1];
-  for (int w = NG - 2; w >= 0; --w) {
-    for (int d = 0; d < c; ++d) acc = xyzz_dbl(acc);
-    acc = xyzz_add(acc, groups[row * NG + w]);
+  G1XYZZ acc = xyzz_inf();
+  for (int w = NG - 1; w >= 0; --w) {
+    if (w != NG - 1)
+      for (int d = 0; d < c; ++d) acc = xyzz_dbl(acc);
+    const G1XYZZ* g = groups + (row * NG + w) * (size_t)split;
+    for (int j = 0; j < split; ++j) acc = xyzz_add(acc, g[j]);
   }
   out[row] = xyzz_to_jac(acc);
 }
@@ -376,12 +434,7 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   size_t max_entries = m * cfg.n * (size_t)cfg.W;
   ZK_REQUIRE(max_entries < 0xffffffffull && nkeys < 0x7fffffffull, ZK_ERR_ARG, "MSM too large for 32-bit entry indices");
   ZK_REQUIRE(!cfg.full || (size_t)cfg.W * cfg.tstep * cfg.n < 0x80000000ull, ZK_ERR_ARG, "table too large");
-  // lanes per bucket: enough threads for ~4 waves of 148 SMs x 512 threads, at most 32
-  size_t want = (size_t)num_sms() * 512 * 2;
-  int Sl = 1; while (Sl < 32 && nkeys * Sl < want && (max_entries / (nkeys * Sl)) >= 8) Sl <<= 1;
-  cfg.S = Sl;
-
-  Scratch counts, offsets, cursors, tiles, total, entries, buckets, groups; int rc;
+  Scratch counts, offsets, cursors, tiles, total, entries, buckets, groups, pcounts, pslot, ptiles, ptotal, partials; int rc;
   unsigned ntiles = div_up(nkeys, SCAN_TILE);
   if ((rc = counts.alloc(sizeof(uint32_t) * nkeys, st))) return rc;
   if ((rc = offsets.alloc(sizeof(uint32_t) * (nkeys + 1), st))) return rc;
@@ -390,7 +443,6 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   if ((rc = total.alloc(sizeof(uint32_t), st))) return rc;
   if ((rc = entries.alloc(sizeof(uint32_t) * max_entries, st))) return rc;
   if ((rc = buckets.alloc(sizeof(G1XYZZ) * nkeys, st))) return rc;
-  if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG, st))) return rc;
 
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * nkeys, st));
   unsigned dgrid = g1_grid(m * cfg.n, 256);
@@ -399,12 +451,34 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(tiles.as<uint32_t>(), ntiles, total.as<uint32_t>()));
   ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(offsets.as<uint32_t>(), cursors.as<uint32_t>(), nkeys, tiles.as<uint32_t>(), total.as<uint32_t>()));
   ZK_LAUNCH(k_msm_digits<true><<<dgrid, 256, 0, st>>>(scalars, cfg, cursors.as<uint32_t>(), entries.as<uint32_t>()));
-  size_t athreads = nkeys * cfg.S;
-  ZK_LAUNCH(k_msm_accumulate<<<div_up(athreads, G1_THREADS), G1_THREADS, 0, st>>>(entries.as<uint32_t>(), offsets.as<uint32_t>(), t->pts,
-                                                                                   buckets.as<G1XYZZ>(), nkeys, cfg.S));
+  // chunked accumulation: about two resident waves of threads, each with the same number of mixed additions
+  uint32_t target = (uint32_t)num_sms() * 384 * 2;
+  Scratch plan, heavy;
+  if ((rc = plan.alloc(sizeof(uint32_t) * 2, st))) return rc;
+  size_t max_heavy = (nkeys + (size_t)target + 2) / (COMBINE_LIGHT + 1) + 1;
+  if ((rc = heavy.alloc(sizeof(uint32_t) * (max_heavy + 1), st))) return rc;
+  ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
+  if ((rc = pcounts.alloc(sizeof(uint32_t) * nkeys, st))) return rc;
+  if ((rc = pslot.alloc(sizeof(uint32_t) * (nkeys + 1), st))) return rc;
+  if ((rc = ptiles.alloc(sizeof(uint32_t) * ntiles, st))) return rc;
+  if ((rc = ptotal.alloc(sizeof(uint32_t), st))) return rc;
+  if ((rc = partials.alloc(sizeof(G1XYZZ) * (nkeys + (size_t)target + 2), st))) return rc;
+  ZK_LAUNCH(k_msm_plan<<<1, 1, 0, st>>>(offsets.as<uint32_t>(), nkeys, target, plan.as<uint32_t>()));
+  ZK_LAUNCH(k_msm_chunk_counts<<<g1_grid(nkeys, 256), 256, 0, st>>>(offsets.as<uint32_t>(), nkeys, plan.as<uint32_t>(), pcounts.as<uint32_t>()));
+  ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(pcounts.as<uint32_t>(), pslot.as<uint32_t>(), nkeys, ptiles.as<uint32_t>()));
+  ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(ptiles.as<uint32_t>(), ntiles, ptotal.as<uint32_t>()));
+  ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(pslot.as<uint32_t>(), pcounts.as<uint32_t>(), nkeys, ptiles.as<uint32_t>(), ptotal.as<uint32_t>()));
+  ZK_LAUNCH(k_msm_accumulate<<<div_up((size_t)target + 1, G1_THREADS), G1_THREADS, 0, st>>>(entries.as<uint32_t>(), offsets.as<uint32_t>(), pslot.as<uint32_t>(),
+                                                                                              t->pts, partials.as<G1XYZZ>(), nkeys, plan.as<uint32_t>()));
+  uint32_t* hcount = heavy.as<uint32_t>(); uint32_t* hlist = hcount + 1;
+  ZK_LAUNCH(k_msm_combine<<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
+  ZK_LAUNCH(k_msm_combine_heavy<<<div_up(max_heavy * 32, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), buckets.as<G1XYZZ>(), hlist, hcount));
+  // reduce: 256-thread CTAs, at most 2 buckets per thread
   int T = cfg.K < 32 ? 32 : (cfg.K > 256 ? 256 : cfg.K);
-  ZK_LAUNCH(k_msm_reduce<<<(unsigned)(m * cfg.NG), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>()));
-  ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, cfg.c, out));
+  int split = cfg.K / (T * 2); if (split < 1) split = 1; if (split > 16) split = 16;
+  if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG * split, st))) return rc;
+  ZK_LAUNCH(k_msm_reduce<<<(unsigned)(m * cfg.NG * split), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, split, groups.as<G1XYZZ>()));
+  ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, split, cfg.c, out));
   return ZK_OK;
 }
 
@@ -433,12 +507,26 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   ZK_REQUIRE(klo < 31 && gens->n == ((size_t)1 << klo), ZK_ERR_DIM, "Incompatible dimensions");   // commitment.cu:89
   // com(u_hi): G1_me == MSM of com against eq(u_hi, .) (g1-tensor.cu:463-491); guard of G1TensorJacobian::operator()(u)
   if (khi > 0) ZK_REQUIRE(!(ncom <= ((size_t)1 << (khi - 1)) || ncom > ((size_t)1 << khi)), ZK_ERR_DIM, "Incompatible dimensions");
+  // com(u_hi) and the opening proper are independent: fork the commitment-vector evaluation onto a side stream so its
+  // latency-bound bucket reduction overlaps the opening MSM (joined before returning).
+  static cudaStream_t side = nullptr; static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  if (!side) {
+    ZK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
   Scratch uq, E, tf; int rc;
-  if ((rc = uq.alloc(sizeof(Fr) * (khi ? khi : 1), st))) return rc;
-  if (khi) ZK_CUDA(cudaMemcpyAsync(uq.p, u_hi, sizeof(Fr) * khi, cudaMemcpyHostToDevice, st));
-  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << khi), st))) return rc;
-  if ((rc = build_eq_table(uq.as<Fr>(), u_hi, (int)khi, 0, E.as<Fr>(), st))) return rc;
-  if ((rc = msm_run(com_table, E.as<Fr>(), 1, 1, 0, com_eval, st))) return rc;
+  ZK_CUDA(cudaEventRecord(ev_fork, st));
+  ZK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  {
+    Scratch uqs, Es;
+    if ((rc = uqs.alloc(sizeof(Fr) * (khi ? khi : 1), side))) return rc;
+    if (khi) ZK_CUDA(cudaMemcpyAsync(uqs.p, u_hi, sizeof(Fr) * khi, cudaMemcpyHostToDevice, side));
+    if ((rc = Es.alloc(sizeof(Fr) * ((size_t)1 << khi), side))) return rc;
+    if ((rc = build_eq_table(uqs.as<Fr>(), u_hi, (int)khi, 0, Es.as<Fr>(), side))) return rc;
+    if ((rc = msm_run(com_table, Es.as<Fr>(), 1, 1, 0, com_eval, side))) return rc;
+  }
+  ZK_CUDA(cudaEventRecord(ev_join, side));
   // t.partial_me(u_hi, |gens|)
   size_t w = gens->n;
   if (khi > 0) ZK_REQUIRE(nt > w * ((size_t)1 << (khi - 1)), ZK_ERR_DIM, "Incompatible dimensions");   // fr-tensor.cu:372
@@ -446,7 +534,9 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   ZK_REQUIRE(tf_n == w, ZK_ERR_DIM, "Incompatible dimensions");                                         // commitment.cu:64
   if ((rc = tf.alloc(sizeof(Fr) * tf_n, st))) return rc;
   if ((rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st))) return rc;
-  return me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
+  rc = me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
+  ZK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+  return rc;
 }
 
 }  // namespace zk

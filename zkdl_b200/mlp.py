@@ -69,9 +69,29 @@ class MLPProver:
                 cur = a
         return self.Z[-1]
 
-    def prove(self, seed=0):
-        """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order."""
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=4):
+        """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
+        fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); challenges are drawn for
+        every layer regardless, so a layer's proof does not depend on which rank produced it.
+        Every layer's proof is independent of the others (all randomness is fresh), so the per-layer
+        proofs are issued round-robin on `streams` CUDA streams: the latency-bound bucket reductions of one layer's
+        opening overlap the bandwidth-bound sumcheck passes of another."""
+        import torch
         ctr = [seed]
+        main = torch.cuda.current_stream()
+        if streams > 1:
+            if len(getattr(self, "_streams", [])) != streams:
+                self._streams = [torch.cuda.Stream() for _ in range(streams)]
+            start = torch.cuda.Event(); start.record(main)
+            for s_ in self._streams:
+                s_.wait_event(start)
+        slot = [0]
+
+        def on_stream():
+            if streams <= 1:
+                return torch.cuda.stream(main)
+            st = self._streams[slot[0] % streams]; slot[0] += 1
+            return torch.cuda.stream(st)
 
         def rv(k):
             ctr[0] += 1
@@ -85,20 +105,32 @@ class MLPProver:
             L = self.layers[i]
             Xin = self.A[i - 1] if i > 0 else self.X
             u_bs, u_in, u_out = rv(kb), rv(ceil_log2(L.I)), rv(ceil_log2(L.O))               # zkfc.cu:135-137
-            out.append(("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, u_bs, u_in, u_out))
+            if fc_layers is not None and i not in fc_layers:
+                return
+            with on_stream():
+                out.append(("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, u_bs, u_in, u_out))
 
         def relu(i):
             n = B * self.layers[i].O
             Lg = ceil_log2(n)
             ch = [rv(Lg + 5), rv(Lg + 5), rv(Lg + 4), rv(Lg + 4), rv(Lg)]                    # zkrelu.cu:85-89
             ch += [rv(Lg), rv(Lg)]                                                           # zkrelu.cu:97-98
+            if relu_layers is not None and i not in relu_layers:
+                return
             sign, mag, rem = self.aux[i]
-            out.append(("relu", i, zk.zkrelu_prove(self.Z[i], sign, mag, rem, *ch)))
+            with on_stream():
+                out.append(("relu", i, zk.zkrelu_prove(self.Z[i], sign, mag, rem, *ch)))
 
         fc(nl - 1)
         for i in range(nl - 2, -1, -1):
             relu(i)
             fc(i)
+        if streams > 1:
+            for s_ in self._streams:
+                ev = torch.cuda.Event(); ev.record(s_); main.wait_event(ev)
+            for part in out:                       # proof tensors were allocated on side streams
+                for t in part[2:]:
+                    t.record_stream(main)
         return out
 
 
