@@ -1,0 +1,166 @@
+"""Reference-generated golden vectors (tests/golden/README.md): pin the CPU oracle (CPU tests) and the CUDA kernels
+(GPU tests) against what the reference's own CUDA code produced on a B200."""
+import os
+import numpy as np
+import pytest
+from oracle import oracle as orc, refio
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+IN = refio.read_box(os.path.join(HERE, "golden", "ref_cases_in.bin"))
+OUT = refio.read_box(os.path.join(HERE, "golden", "ref_cases_out.bin"))
+
+
+def fr(name, box=None):
+    return (box or IN)[name].reshape(-1, 8)
+
+
+def g1(name, box=None):
+    return (box or IN)[name].reshape(-1, 36)
+
+
+def same_points(a, b):
+    return orc.g1_eq(np.asarray(a).reshape(-1, 36), np.asarray(b).reshape(-1, 36)).all()
+
+
+def test_reference_ran_clean():
+    assert OUT["cuda_status"][0] == 0
+
+
+# ------------------------------------------------------------------------------------------- oracle vs reference (CPU)
+def test_oracle_fr_ops():
+    a, b, x = fr("ops.a"), fr("ops.b"), fr("ops.x")
+    assert np.array_equal(orc.fr_add(a, b), fr("ops.add", OUT))
+    assert np.array_equal(orc.fr_sub(a, b), fr("ops.sub", OUT))
+    assert np.array_equal(orc.fr_mul(a, b), fr("ops.mul", OUT))
+    assert np.array_equal(orc.fr_neg(a), fr("ops.neg", OUT))
+    assert np.array_equal(orc.fr_mont(a), fr("ops.mont", OUT))
+    assert np.array_equal(orc.fr_unmont(a), fr("ops.unmont", OUT))
+    assert np.array_equal(orc.fr_bcast(a, x, "add"), fr("ops.badd", OUT))
+    assert np.array_equal(orc.fr_bcast(a, x, "sub"), fr("ops.bsub", OUT))
+    assert np.array_equal(orc.fr_bcast(a, x, "mul"), fr("ops.bmul", OUT))
+    assert np.array_equal(orc.fr_sum(a), OUT["ops.sum"])
+
+
+def test_oracle_folds_and_sumchecks():
+    a, u = fr("fold.a"), fr("fold.u")
+    w, kk = (int(v) for v in IN["fold.w"])
+    assert np.array_equal(orc.fr_me(a, u), OUT["fold.me"])
+    assert np.array_equal(orc.fr_partial_me(a, u[:kk], w), fr("fold.pm", OUT))
+    a, b, u, v = fr("sc.a"), fr("sc.b"), fr("sc.u"), fr("sc.v")
+    assert np.array_equal(orc.ip_sumcheck(a, b, u), fr("sc.ip", OUT))
+    assert np.array_equal(orc.hp_sumcheck(a, b, u, v), fr("sc.hp", OUT))
+    assert np.array_equal(orc.bin_sumcheck(a, u, v), fr("sc.bin", OUT))
+
+
+def test_oracle_g1_bit_exact_jacobian():
+    p, q, x, u = g1("g1.p"), g1("g1.q"), fr("g1.x"), fr("g1.u")
+    # same formula sequence as the reference => identical Jacobian limbs, not just the same points
+    assert np.array_equal(orc.g1_add(p, q), g1("g1.add", OUT))
+    assert np.array_equal(orc.g1_add(p, orc.g1_neg(q)), g1("g1.sub", OUT))
+    assert np.array_equal(orc.g1_neg(p), g1("g1.neg", OUT))
+    assert np.array_equal(orc.g1_mul(p, x), g1("g1.mul", OUT))
+    assert np.array_equal(orc.g1_sum(p), g1("g1.sum", OUT))
+    assert np.array_equal(orc.g1_me(p, u), g1("g1.me", OUT))
+    assert same_points(orc.g1_mul(p, x, fast=True), g1("g1.mul", OUT))
+
+
+def test_oracle_commitment():
+    G, t = g1("com.g"), fr("com.t")
+    assert np.array_equal(orc.commit(G, t), g1("com.rows", OUT))
+    # Commitment::commit as written: only rows 64*b are defined
+    aw = orc.commit_as_written(G, t)
+    assert np.array_equal(aw[::64], g1("com.as_written", OUT)[::64])
+    assert not same_points(aw[:1], g1("com.rows", OUT)[:1])          # and it is NOT the row commitment
+    proof, ret = orc.me_open(fr("com.s"), G, fr("com.u"))
+    assert np.array_equal(proof, g1("com.open_proof", OUT)) and np.array_equal(ret, OUT["com.open_ret"])
+    g_eval, proof, ret = orc.open_(t, G, g1("com.rows", OUT), fr("com.uo"))
+    assert np.array_equal(g_eval, g1("com.eval", OUT))
+    assert np.array_equal(proof, g1("com.full_proof", OUT)) and np.array_equal(ret, OUT["com.full_ret"])
+    assert np.array_equal(ret, OUT["com.open_api_ret"])
+
+
+def _fc_inputs():
+    B, I, O, ng = (int(v) for v in IN["fc.dims"])
+    w = IN["fc.w"].view(np.float32).reshape(I, O)
+    x = IN["fc.x"].view(np.float32).reshape(B, I)
+    return B, I, O, w, x
+
+
+def test_oracle_quantise_forward_relu():
+    B, I, O, w, x = _fc_inputs()
+    Bp, Ip, Op = 4, 16, 8
+    wq, xq = orc.float_to_fr(w, Ip, Op), orc.float_to_fr(x, Bp, Ip)
+    assert np.array_equal(wq, fr("fc.wq", OUT)) and np.array_equal(xq, fr("fc.xq", OUT))
+    Z = orc.fr_matmul(orc.fr_mont(xq), orc.fr_mont(wq), Bp, Ip, Op)
+    assert np.array_equal(Z, fr("fc.z", OUT))
+    A, sign, mag, rem, bad = orc.relu(Z)
+    assert bad == 0
+    assert np.array_equal(A, fr("relu.a", OUT)) and np.array_equal(sign, fr("relu.sign", OUT))
+    assert np.array_equal(mag, fr("relu.mag", OUT)) and np.array_equal(rem, fr("relu.rem", OUT))
+
+
+# ------------------------------------------------------------------------------------------- CUDA vs reference (GPU)
+@pytest.fixture(scope="module")
+def zk():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from zkdl_b200 import capi
+    capi.lib()
+    return capi
+
+
+@pytest.mark.gpu
+def test_cuda_fr_and_sumchecks_vs_reference(zk):
+    a, b, x = zk.to_device(fr("ops.a")), zk.to_device(fr("ops.b")), fr("ops.x")
+    for op, name in ((zk.OP_ADD, "ops.add"), (zk.OP_SUB, "ops.sub"), (zk.OP_MUL, "ops.mul")):
+        assert np.array_equal(zk.to_host(zk.fr_elementwise(op, a, b)), fr(name, OUT))
+    for op, name in ((zk.OP_NEG, "ops.neg"), (zk.OP_MONT, "ops.mont"), (zk.OP_UNMONT, "ops.unmont")):
+        assert np.array_equal(zk.to_host(zk.fr_elementwise(op, a)), fr(name, OUT))
+    for op, name in ((zk.OP_ADD, "ops.badd"), (zk.OP_SUB, "ops.bsub"), (zk.OP_MUL, "ops.bmul")):
+        assert np.array_equal(zk.to_host(zk.fr_broadcast(op, a, x)), fr(name, OUT))
+    assert np.array_equal(zk.to_host(zk.fr_sum(a))[0], OUT["ops.sum"])
+    fa, u = zk.to_device(fr("fold.a")), fr("fold.u")
+    w, kk = (int(v) for v in IN["fold.w"])
+    assert np.array_equal(zk.to_host(zk.fr_me(fa, u))[0], OUT["fold.me"])
+    assert np.array_equal(zk.to_host(zk.fr_partial_me(fa, u[:kk], w)), fr("fold.pm", OUT))
+    sa, sb = zk.to_device(fr("sc.a")), zk.to_device(fr("sc.b"))
+    assert np.array_equal(zk.to_host(zk.ip_sumcheck(sa, sb, fr("sc.u"))), fr("sc.ip", OUT))
+    assert np.array_equal(zk.to_host(zk.hp_sumcheck(sa, sb, fr("sc.u"), fr("sc.v"))), fr("sc.hp", OUT))
+    assert np.array_equal(zk.to_host(zk.bin_sumcheck(sa, fr("sc.u"), fr("sc.v"))), fr("sc.bin", OUT))
+
+
+@pytest.mark.gpu
+def test_cuda_g1_and_commitment_vs_reference(zk):
+    p, q, x = zk.to_device(g1("g1.p")), zk.to_device(g1("g1.q")), zk.to_device(fr("g1.x"))
+    assert same_points(zk.to_host(zk.g1_elementwise(zk.G1_ADD, p, q)), g1("g1.add", OUT))
+    assert same_points(zk.to_host(zk.g1_elementwise(zk.G1_SUB, p, q)), g1("g1.sub", OUT))
+    assert same_points(zk.to_host(zk.g1_elementwise(zk.G1_NEG, p)), g1("g1.neg", OUT))
+    assert same_points(zk.to_host(zk.g1_mul(p, x)), g1("g1.mul", OUT))
+    assert same_points(zk.to_host(zk.g1_sum(p)), g1("g1.sum", OUT))
+    assert same_points(zk.to_host(zk.g1_me(p, fr("g1.u"))), g1("g1.me", OUT))
+    G, t = zk.to_device(g1("com.g")), zk.to_device(fr("com.t"))
+    gens = zk.G1Table(G, full=True)
+    com = zk.commit(gens, t)
+    assert same_points(zk.to_host(com), g1("com.rows", OUT))
+    proof, ret = zk.me_open(gens, zk.to_device(fr("com.s")), fr("com.u"))
+    assert same_points(zk.to_host(proof), g1("com.open_proof", OUT)) and np.array_equal(zk.to_host(ret)[0], OUT["com.open_ret"])
+    com_tab = zk.G1Table(com, full=True)
+    ev, proof, ret = zk.open_(gens, com_tab, t, fr("com.uo"))
+    assert same_points(zk.to_host(ev), g1("com.eval", OUT))
+    assert same_points(zk.to_host(proof), g1("com.full_proof", OUT)) and np.array_equal(zk.to_host(ret)[0], OUT["com.full_ret"])
+    gens.close(); com_tab.close()
+
+
+@pytest.mark.gpu
+def test_cuda_forward_vs_reference(zk):
+    import torch
+    B, I, O, w, x = _fc_inputs()
+    wq = zk.float_to_fr(torch.from_numpy(w).cuda(), 16, 8)
+    xq = zk.float_to_fr(torch.from_numpy(x).cuda(), 4, 16)
+    assert np.array_equal(zk.to_host(wq), fr("fc.wq", OUT)) and np.array_equal(zk.to_host(xq), fr("fc.xq", OUT))
+    Z = zk.fr_matmul(zk.fr_elementwise(zk.OP_MONT, xq), zk.fr_elementwise(zk.OP_MONT, wq), 4, 16, 8)
+    assert np.array_equal(zk.to_host(Z), fr("fc.z", OUT))
+    A, sign, mag, rem, bad = zk.relu(Z)
+    assert np.array_equal(zk.to_host(A), fr("relu.a", OUT)) and np.array_equal(zk.to_host(sign), fr("relu.sign", OUT))
+    assert np.array_equal(zk.to_host(mag), fr("relu.mag", OUT)) and np.array_equal(zk.to_host(rem), fr("relu.rem", OUT))
