@@ -6,6 +6,9 @@
 // that (a) tests/golden/*.bin are produced by the reference's own CUDA code on a B200 and (b) the GPU test-suite can
 // diff the new kernels against the reference live.  It also provides the Baseline-A timing loops of BASELINE.md.
 //
+// The same source also compiles, unchanged, against the drop-in headers of zkdl_b200/host (-DZKDL_HOST_BUILD,
+// -Izkdl_b200/host): that binary (zkdl_b200/host/zk_harness) is the API-level parity and timing twin of this one.
+//
 //   ref_harness run  <in.bin> <out.bin>     execute every case present in the input container
 //   ref_harness time <what> <args...>       print one JSON line with reference timings
 //
@@ -23,11 +26,13 @@
 #include <random>
 #include <stdexcept>
 #include <cuda_runtime.h>
-#include <curand_kernel.h>
 #include <iomanip>
 #include <utility>
+#ifndef ZKDL_HOST_BUILD      // building against the reference: its headers need these (zkfc.cuh pulls in LibTorch)
+#include <curand_kernel.h>
 #include <torch/torch.h>
 #include <torch/script.h>
+#endif
 // the reference keeps device pointers private; the harness needs bulk copies (reference files are not modified)
 #define private public
 #define protected public

@@ -164,3 +164,26 @@ def test_cuda_forward_vs_reference(zk):
     A, sign, mag, rem, bad = zk.relu(Z)
     assert np.array_equal(zk.to_host(A), fr("relu.a", OUT)) and np.array_equal(zk.to_host(sign), fr("relu.sign", OUT))
     assert np.array_equal(zk.to_host(mag), fr("relu.mag", OUT)) and np.array_equal(zk.to_host(rem), fr("relu.rem", OUT))
+
+
+# ------------------------------------------------------------------------------------------- drop-in C++ API vs reference (GPU)
+@pytest.mark.gpu
+def test_host_api_harness_vs_reference(tmp_path):
+    """oracle/ref_harness.cu is written against the reference's C++ API.  Compiled unchanged against the drop-in headers
+    (zkdl_b200/host/zk_harness) it must reproduce the arrays the reference build produced."""
+    import subprocess, torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    exe = os.path.join(os.path.dirname(HERE), "zkdl_b200", "host", "zk_harness")
+    assert os.path.exists(exe), "zkdl_b200/host/zk_harness missing: run __graft_entry__.build()"
+    out_path = str(tmp_path / "out.bin")
+    subprocess.check_call([exe, "run", os.path.join(HERE, "golden", "ref_cases_in.bin"), out_path])
+    got = refio.read_box(out_path)
+    assert got["cuda_status"][0] == 0
+    fr_names = [k for k in OUT if k.startswith(("ops.", "fold.", "sc.", "fc.", "relu.")) or k in ("com.open_ret", "com.full_ret", "com.open_api_ret")]
+    for k in fr_names:
+        assert np.array_equal(got[k], OUT[k]), k
+    for k in ("g1.add", "g1.sub", "g1.neg", "g1.mul", "g1.sum", "g1.me", "com.rows", "com.open_proof", "com.eval", "com.full_proof"):
+        assert same_points(got[k], OUT[k]), k
+    # Commitment::commit: the drop-in returns the intended row commitments, not the reference's as-written rows
+    assert same_points(got["com.as_written"], OUT["com.rows"])

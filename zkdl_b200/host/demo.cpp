@@ -1,0 +1,95 @@
+// demo.cpp — the drop-in entry  ./demo traced_model.pt sample_input.pt  (replaces /root/reference/demo.cu:23-143).
+// Host code only: LibTorch reads the two TorchScript files, everything else goes through the reference-named classes of
+// zkdl.hpp, i.e. through the C ABI of libzkdl_b200.so.  Same observable behaviour: writes demo.out (the un-Montgomery'd
+// last-layer output, one 0x%064x value per line), prints "Total number of parameters", "Proof time: ... seconds per
+// data point." and "Current CUDA status".  Extras: ZKDL_SEED=<n> makes generators and challenges reproducible,
+// ZKDL_DUMP_PROOF=<file> writes every proof element (the reference discards them).
+#include <torch/script.h>
+#include <torch/torch.h>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+#include "zkdl.hpp"
+
+using namespace std;
+
+static FrTensor fcnn_inference(const FrTensor& X, const vector<zkFC>& fcs, vector<zkReLU>& relus, vector<FrTensor>& Z_vec, vector<FrTensor>& A_vec) {
+  if (fcs.size() != relus.size() + 1) throw std::runtime_error("Incompatible number of layers");
+  size_t num_layer = fcs.size();
+  Z_vec.reserve(num_layer); A_vec.reserve(num_layer);
+  for (size_t i = 0; i + 1 < num_layer; ++i) {
+    const FrTensor& A = (i == 0) ? X : A_vec[i - 1];
+    Z_vec.push_back(fcs[i](A));
+    A_vec.push_back(relus[i](Z_vec[i]));
+  }
+  return fcs[num_layer - 1](A_vec[num_layer - 2]);
+}
+
+static vector<zkFC> load_model(const string& model_path, vector<Commitment>& generators) {
+  vector<zkFC> fcs;
+  torch::jit::script::Module m;
+  try { m = torch::jit::load(model_path); } catch (const c10::Error& e) { std::cerr << "Error loading the model\n"; exit(-1); }
+  uint parameter_count = 0;
+  for (int i = 0;; ++i) {
+    if (!m.hasattr(to_string(i))) break;
+    auto child = m.attr(to_string(i)).toModule();
+    if (!child.hasattr("weight")) continue;                                   // ReLU
+    torch::Tensor weight = child.attr("weight").toTensor().t().contiguous();  // [in, out]; kept alive (the reference reads a temporary)
+    if (!weight.is_cuda()) throw std::runtime_error("Weight tensor is not on GPU");
+    int in_dim = weight.size(0), out_dim = weight.size(1);
+    parameter_count += in_dim * out_dim;
+    generators.push_back({1U << ((ceilLog2(in_dim * out_dim) + 1) / 2), G1Jacobian_generator});
+    generators.back() *= FrTensor::random(generators.back().size);
+    fcs.push_back(zkFC::from_float_gpu_ptr(in_dim, out_dim, weight.data_ptr<float>(), generators.back()));
+    if (fcs.size() > 1 && fcs[fcs.size() - 2].outputSize != fcs[fcs.size() - 1].inputSize) throw std::runtime_error("Incompatible layer sizes");
+  }
+  cout << "Total number of parameters: " << parameter_count << endl;
+  return fcs;
+}
+
+int main(int argc, char* argv[]) {
+  if (argc < 3) { cerr << "usage: demo <traced_model.pt> <sample_input.pt>" << endl; return 2; }
+  if (const char* s = getenv("ZKDL_SEED")) set_challenge_seed((uint32_t)atoi(s));
+  vector<Commitment> generators; generators.reserve(64);
+  vector<zkFC> fcs = load_model(argv[1], generators);
+  vector<zkReLU> relus(fcs.size() - 1);
+  vector<FrTensor> Z_vec, A_vec;
+
+  torch::Tensor sample_input;
+  torch::load(sample_input, argv[2]);
+  sample_input = sample_input.contiguous();
+  if (!sample_input.is_cuda()) throw std::runtime_error("Sample input tensor is not on GPU");
+  int batch_size = sample_input.size(0), input_dim = sample_input.size(1);
+  auto X = zkFC::load_float_gpu_input(batch_size, input_dim, sample_input.data_ptr<float>());
+
+  auto Y_hat = fcnn_inference(X.mont(), fcs, relus, Z_vec, A_vec).unmont();
+  { ofstream outfile("demo.out"); outfile << Y_hat << endl; }
+
+  Timer timer;
+  cudaDeviceSynchronize();
+  timer.start();
+  size_t num_layer = fcs.size();
+  fcs[num_layer - 1].prove(A_vec[num_layer - 2], Y_hat, generators[num_layer - 1]);
+  for (int i = (int)num_layer - 2; i >= 0; --i) {
+    relus[i].prove(Z_vec[i], A_vec[i]);
+    FrTensor& A_ = (i > 0) ? A_vec[i - 1] : X;
+    fcs[i].prove(A_, Z_vec[i], generators[i]);
+  }
+  cudaDeviceSynchronize();
+  timer.stop();
+  cout << "Proof time: " << timer.getTotalTime() / batch_size << " seconds per data point." << endl;
+  cout << "Current CUDA status: " << cudaGetLastError() << endl;
+
+  if (const char* path = getenv("ZKDL_DUMP_PROOF")) {
+    ofstream pf(path);
+    for (int i = (int)num_layer - 1; i >= 0; --i) {
+      pf << "fc " << i << "\n";
+      for (auto& x : fcs[i].last_proof_fr()) pf << x << "\n";
+      for (auto& g : fcs[i].last_proof_g1()) pf << g << "\n";
+      if (i > 0) { pf << "relu " << i - 1 << "\n"; for (auto& x : relus[i - 1].last_proof()) pf << x << "\n"; }
+    }
+  }
+  return 0;
+}
