@@ -70,6 +70,12 @@ int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t 
  * reference) give sign = 0, mag = 0 and are counted in *out_of_range (device u32, may be NULL). */
 int zkdl_relu(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, uint32_t* out_of_range, void* stream);
 
+/* Same decomposition with the auxiliary input kept bit-packed (48 bits instead of 1536 B per activation):
+ * mag_packed[i] = the 32 mag_bin cells of element i (bit k = cell 32i+k), rem_packed[i] = its 16 rem_bin cells.
+ * zkdl_relu_expand materialises the reference's 0/1 Fr tables from the packed words (either output may be NULL). */
+int zkdl_relu_packed(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, uint32_t* mag_packed, uint16_t* rem_packed, size_t n, uint32_t* out_of_range, void* stream);
+int zkdl_relu_expand(const uint32_t* mag_packed, const uint16_t* rem_packed, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, void* stream);
+
 /* ------------------------------------------------------------------ G1 tensors (g1-tensor.cu) */
 enum { ZKDL_G1_ADD = 0, ZKDL_G1_SUB = 1, ZKDL_G1_NEG = 2, ZKDL_G1_MADD = 3, ZKDL_G1_MSUB = 4 };
 /* G1_jacobian_elementwise_{add,sub,madd,msub,minus} and the broadcast forms (g1-tensor.cu:169-302):
@@ -125,6 +131,13 @@ int zkdl_zkrelu_prove(const zkdl_fr_t* X, const zkdl_fr_t* sign, const zkdl_fr_t
                       const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
                       const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
                       zkdl_fr_t* proof_fr, void* stream);
+
+/* zkReLU::prove on the packed auxiliary input: identical proof elements (the cells are exactly Scalar_ONE/ZERO,
+ * zkrelu.cu:34-38), first three binary-sumcheck rounds and both partial_me calls read 48 bits per activation. */
+int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const uint32_t* mag_packed, const uint16_t* rem_packed, size_t n,
+                             const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
+                             const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
+                             zkdl_fr_t* proof_fr, void* stream);
 
 /* ------------------------------------------------------------------ host helpers (proof.cu:3-31) */
 /* random_vec with an injected seed: std::mt19937(seed), 8 draws per element, last % 1944954707 */

@@ -241,7 +241,7 @@ def test_zkfc_prove_and_open(zk, B, I, O):
     gens.close(); com_tab.close()
 
 
-@pytest.mark.parametrize("n", [64, 4096])
+@pytest.mark.parametrize("n", [2, 64, 4096, 1 << 15])
 def test_zkrelu_prove(zk, n):
     L = orc.ceil_log2(n)
     xs = [int(v) for v in rng.integers(-(1 << 40), 1 << 40, size=n)]
@@ -254,6 +254,13 @@ def test_zkrelu_prove(zk, n):
     ref = orc.zkrelu_prove(X, osign, omag, orem, *ch)
     exp = np.concatenate([ref["mag_sc"], ref["mag_rec"], ref["rem_sc"], ref["rem_rec"], ref["hp"]])
     assert eq(got, exp)
+    # packed auxiliary input: same proof from 48 bits per activation
+    Z2, sign2, magp, remp, bad2 = zk.relu_packed(dX)
+    assert eq(zk.to_host(Z2), oZ) and eq(zk.to_host(sign2), osign)
+    mag2, rem2 = zk.relu_expand(magp, remp)
+    assert eq(zk.to_host(mag2), omag) and eq(zk.to_host(rem2), orem)
+    got2 = zk.to_host(zk.zkrelu_prove_packed(dX, sign2, magp, remp, *ch))
+    assert eq(got2, exp)
 
 
 def test_random_vec_matches_oracle(zk):

@@ -231,6 +231,24 @@ def relu(X):
     return Z, sign, mag, rem, bad
 
 
+def relu_packed(X):
+    """Z, sign, packed mag (int32 [n]), packed rem (int16 [n]), out-of-range counter."""
+    torch = _torch()
+    n = X.shape[0]
+    Z, sign = empty(n, 8), empty(n, 8)
+    mag = torch.empty(n, dtype=torch.int32, device="cuda"); rem = torch.empty(n, dtype=torch.int16, device="cuda")
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _check(lib().zkdl_relu_packed(_ptr(X), _ptr(Z), _ptr(sign), _ptr(mag), _ptr(rem), _sz(n), _ptr(bad), _stream()))
+    return Z, sign, mag, rem, bad
+
+
+def relu_expand(mag_packed, rem_packed):
+    n = mag_packed.shape[0]
+    mag, rem = empty(32 * n, 8), empty(16 * n, 8)
+    _check(lib().zkdl_relu_expand(_ptr(mag_packed), _ptr(rem_packed), _ptr(mag), _ptr(rem), _sz(n), _stream()))
+    return mag, rem
+
+
 # ------------------------------------------------------------------ G1
 def g1_elementwise(op, a, b=None):
     out = empty(a.shape[0], 36)
@@ -348,6 +366,14 @@ def zkrelu_prove(X, sign, mag_bin, rem_bin, u_z, v_z, u_r, v_r, u_rec, u_hp, v_h
     pfr = empty(lib().zkdl_zkrelu_proof_size(n), 8)
     hs = [_host_fr(a) for a in (u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp)]
     _check(lib().zkdl_zkrelu_prove(_ptr(X), _ptr(sign), _ptr(mag_bin), _ptr(rem_bin), _sz(n), *[h[1] for h in hs], _ptr(pfr), _stream()))
+    return pfr
+
+
+def zkrelu_prove_packed(X, sign, mag_packed, rem_packed, u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp):
+    n = X.shape[0]
+    pfr = empty(lib().zkdl_zkrelu_proof_size(n), 8)
+    hs = [_host_fr(a) for a in (u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp)]
+    _check(lib().zkdl_zkrelu_prove_packed(_ptr(X), _ptr(sign), _ptr(mag_packed), _ptr(rem_packed), _sz(n), *[h[1] for h in hs], _ptr(pfr), _stream()))
     return pfr
 
 

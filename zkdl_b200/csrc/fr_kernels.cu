@@ -523,4 +523,21 @@ int zkdl_relu(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, zkdl_fr_t* mag_
   return ZK_OK;
 }
 
+
+int zkdl_relu_packed(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, uint32_t* mag_packed, uint16_t* rem_packed, size_t n, uint32_t* out_of_range, void* stream) {
+  cudaStream_t st = S(stream);
+  if (n == 0) return ZK_OK;
+  ZK_REQUIRE(X && Z && sign && mag_packed && rem_packed, ZK_ERR_ARG, "null argument");
+  if (out_of_range) ZK_CUDA(cudaMemsetAsync(out_of_range, 0, sizeof(uint32_t), st));
+  ZK_LAUNCH(k_relu<<<stream_grid(n, THREADS), THREADS, 0, st>>>(F(X), F(Z), F(sign), mag_packed, rem_packed, n, out_of_range));
+  return ZK_OK;
+}
+int zkdl_relu_expand(const uint32_t* mag_packed, const uint16_t* rem_packed, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, void* stream) {
+  cudaStream_t st = S(stream);
+  if (n == 0) return ZK_OK;
+  if (mag_bin) ZK_LAUNCH(k_expand_bits<32, uint32_t><<<stream_grid(n * 32, THREADS), THREADS, 0, st>>>(mag_packed, F(mag_bin), n * 32));
+  if (rem_bin) ZK_LAUNCH(k_expand_bits<16, uint16_t><<<stream_grid(n * 16, THREADS), THREADS, 0, st>>>(rem_packed, F(rem_bin), n * 16));
+  return ZK_OK;
+}
+
 }  // extern "C"

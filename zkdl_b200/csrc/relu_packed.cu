@@ -1,0 +1,259 @@
+// relu_packed.cu — zkReLU proof on the bit-packed auxiliary input.
+//
+// The reference stores the ReLU decomposition as 0/1 Fr tables (mag_bin: 32 cells, rem_bin: 16 cells per activation,
+// 1.5 KB per element, /root/reference/zkrelu.cu:30-38) and runs the generic binary sumcheck over them
+// (/root/reference/zkrelu.cu:91-94 -> proof.cu:152-200): the largest HBM consumer of the whole proof.
+// The cells are exactly Scalar_ONE / Scalar_ZERO, so the same proof elements can be produced from 48 bits per element:
+//   * rounds 0..2 of the binary sumcheck only ever see tables whose entries are functions of 2 / 4 / 8 original bits.
+//     With eq(u[j+1:], g) = eq_lo(j, group-in-element) * eq_hi(element), round j's three coefficients are
+//     sum_elem eq_hi[elem] * sum_groups LUT_j[group][bit pattern], i.e. table look-ups + additions and 7 products per
+//     ELEMENT for all three rounds together, instead of 6 products per CELL PAIR per round.
+//   * after three rounds each table entry is V3[byte]; the folded table a^(3) (1/8 of the cells) is materialised in the
+//     same pass and the generic single-pass rounds (fr_kernels.cu) take over.
+//   * mag_bin.partial_me(u, 32) / rem_bin.partial_me(u, 16) (zkrelu.cu:92,94) are per-bit sums of eq(u, elem).
+// All values are the same field elements the reference computes, so the proof is bit-identical (tests/test_gpu_parity.py).
+#include <atomic>
+#include "common.cuh"
+#include "fr_device.cuh"
+#include "../../include/zkdl_b200.h"
+
+namespace zk {
+extern std::atomic<uint64_t> g_launches;
+#define ZK_LAUNCH(...)            \
+  do {                            \
+    __VA_ARGS__;                  \
+    zk::g_launches.fetch_add(1);  \
+    ZK_CHECK_LAUNCH();            \
+  } while (0)
+
+int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
+
+template <int Q> struct PackLayout {
+  static constexpr int LOGQ = Q == 32 ? 5 : 4;
+  static constexpr int N0 = Q / 2, N1 = Q / 4, N2 = Q / 8;
+  static constexpr int OFF_E0 = 0;                         // eq_lo of round 0: N0 entries
+  static constexpr int OFF_L1 = OFF_E0 + N0;               // [N1][16][3]
+  static constexpr int OFF_L2 = OFF_L1 + N1 * 16 * 3;      // [N2][256][3]
+  static constexpr int OFF_V3 = OFF_L2 + N2 * 256 * 3;     // [256]
+  static constexpr int TOTAL = OFF_V3 + 256;
+};
+
+// unweighted Fr_bin_sc_step coefficients of a pair (proof.cu:152-163)
+__device__ __forceinline__ void bin_coeffs(const Fr& x0, const Fr& x1, Fr* c) {
+  Fr d = sub(x1, x0);
+  c[0] = sub(mul(x0, x0), x0);
+  c[1] = sub(mul(dbl(x0), d), d);
+  c[2] = mul(d, d);
+}
+// eq(q[0..t), idx): q[0] binds bit 0
+__device__ __forceinline__ Fr eq_point(const Fr* q, int t, unsigned idx) {
+  Fr r = Fr::one();
+  for (int i = 0; i < t; ++i) r = mul(r, ((idx >> i) & 1u) ? q[i] : sub(Fr::one(), q[i]));
+  return r;
+}
+
+// Builds the look-up tables of the three packed rounds from the challenges (single CTA).
+template <int Q>
+__global__ void __launch_bounds__(256) k_bin_luts(const Fr* __restrict__ u, const Fr* __restrict__ v, Fr* __restrict__ lut) {
+  using PL = PackLayout<Q>;
+  __shared__ Fr V1[4], V2[16], e1[PL::N1], e2[PL::N2];
+  const int tid = threadIdx.x;
+  if (tid < 4) {
+    Fr x0 = (tid & 1) ? Fr::one() : Fr::zero(), x1 = (tid >> 1) ? Fr::one() : Fr::zero();
+    V1[tid] = fold_pair(x0, x1, v[0]);
+  }
+  if (tid < PL::N0) lut[PL::OFF_E0 + tid] = eq_point(u + 1, PL::LOGQ - 1, tid);
+  if (tid < PL::N1) e1[tid] = eq_point(u + 2, PL::LOGQ - 2, tid);
+  if (tid < PL::N2) e2[tid] = eq_point(u + 3, PL::LOGQ - 3, tid);
+  __syncthreads();
+  if (tid < 16) V2[tid] = fold_pair(V1[tid & 3], V1[tid >> 2], v[1]);
+  __syncthreads();
+  // round 1 tables: pattern = nibble -> pair (V1[lo 2 bits], V1[hi 2 bits])
+  for (int i = tid; i < PL::N1 * 16; i += blockDim.x) {
+    int t = i / 16, nib = i % 16; Fr c[3];
+    bin_coeffs(V1[nib & 3], V1[nib >> 2], c);
+    for (int k = 0; k < 3; ++k) lut[PL::OFF_L1 + i * 3 + k] = mul(e1[t], c[k]);
+  }
+  // round 2 tables: pattern = byte -> pair (V2[lo nibble], V2[hi nibble]);  V3[byte] = fold of that pair with v[2]
+  for (int byte = tid; byte < 256; byte += blockDim.x) {
+    Fr x0 = V2[byte & 15], x1 = V2[byte >> 4], c[3];
+    bin_coeffs(x0, x1, c);
+    for (int t = 0; t < PL::N2; ++t)
+      for (int k = 0; k < 3; ++k) lut[PL::OFF_L2 + (t * 256 + byte) * 3 + k] = mul(e2[t], c[k]);
+    lut[PL::OFF_V3 + byte] = fold_pair(x0, x1, v[2]);
+  }
+}
+
+extern __shared__ __align__(16) unsigned char pk_smem[];
+
+// One pass over the packed words: rounds 0, 1, 2 of the binary sumcheck + the folded table a^(3).
+// partials[blockIdx][7] = {S0, S1[3], S2[3]}
+template <int Q, class T>
+__global__ void __launch_bounds__(256) k_bin_packed3(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e_hi, const Fr* __restrict__ lut,
+                                                     Fr* __restrict__ a3, Fr* __restrict__ partials) {
+  using PL = PackLayout<Q>;
+  Fr* sm = reinterpret_cast<Fr*>(pk_smem);
+  for (int i = threadIdx.x; i < PL::TOTAL; i += blockDim.x) sm[i] = lut[i];
+  __syncthreads();
+  const Fr* E0 = sm + PL::OFF_E0; const Fr* L1 = sm + PL::OFF_L1; const Fr* L2 = sm + PL::OFF_L2; const Fr* V3 = sm + PL::OFF_V3;
+  Fr acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = Fr::zero();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w = packed[i];
+    Fr eh = e_hi[i];
+    Fr s0 = Fr::zero();
+    uint32_t diff = (w ^ (w >> 1));                       // bit 2t set <=> cells 2t, 2t+1 differ
+#pragma unroll 4
+    for (int t = 0; t < PL::N0; ++t) if ((diff >> (2 * t)) & 1u) s0 = add(s0, E0[t]);
+    Fr s1[3] = {Fr::zero(), Fr::zero(), Fr::zero()}, s2[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+#pragma unroll 2
+    for (int t = 0; t < PL::N1; ++t) {
+      const Fr* e = L1 + (t * 16 + ((w >> (4 * t)) & 15u)) * 3;
+      s1[0] = add(s1[0], e[0]); s1[1] = add(s1[1], e[1]); s1[2] = add(s1[2], e[2]);
+    }
+#pragma unroll
+    for (int t = 0; t < PL::N2; ++t) {
+      uint32_t byte = (w >> (8 * t)) & 255u;
+      const Fr* e = L2 + (t * 256 + byte) * 3;
+      s2[0] = add(s2[0], e[0]); s2[1] = add(s2[1], e[1]); s2[2] = add(s2[2], e[2]);
+      a3[i * PL::N2 + t] = V3[byte];
+    }
+    acc[0] = add(acc[0], mul(eh, s0));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { acc[1 + k] = add(acc[1 + k], mul(eh, s1[k])); acc[4 + k] = add(acc[4 + k], mul(eh, s2[k])); }
+  }
+  __shared__ Fr red[3 * 32];
+  block_reduce_fr<3>(acc, red);
+  __syncthreads();
+  block_reduce_fr<3>(acc + 3, red);
+  __syncthreads();
+  block_reduce_fr<1>(acc + 6, red);
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) partials[blockIdx.x * 7 + k] = acc[k];
+}
+// proof[0..8] from the per-CTA partials: (0, -S0, S0), S1, S2
+__global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict__ partials, unsigned nparts, Fr* __restrict__ proof) {
+  __shared__ Fr red[3 * 32];
+  Fr acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = Fr::zero();
+  for (unsigned i = threadIdx.x; i < nparts; i += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[k] = add(acc[k], partials[(size_t)i * 7 + k]);
+  block_reduce_fr<3>(acc, red);
+  __syncthreads();
+  block_reduce_fr<3>(acc + 3, red);
+  __syncthreads();
+  block_reduce_fr<1>(acc + 6, red);
+  if (threadIdx.x == 0) {
+    proof[0] = Fr::zero(); proof[1] = neg(acc[0]); proof[2] = acc[0];
+    for (int k = 0; k < 6; ++k) proof[3 + k] = acc[1 + k];
+  }
+}
+
+// partial_me(u, Q) of a 0/1 table: out[bit] = sum over elements with that bit set of eq(u, elem).  Lane = bit.
+template <int Q, class T>
+__global__ void __launch_bounds__(256) k_packed_recover(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e, Fr* __restrict__ partials) {
+  constexpr int EPW = 32 / Q;                               // elements per warp iteration
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int bit = lane % Q, sub = lane / Q;
+  Fr acc = Fr::zero();
+  size_t wid = (size_t)blockIdx.x * nwarps + warp, nw = (size_t)gridDim.x * nwarps;
+  for (size_t base = wid * EPW; base < n; base += nw * EPW) {
+    size_t i = base + sub;
+    if (i < n && ((packed[i] >> bit) & 1u)) acc = add(acc, e[i]);
+  }
+  __shared__ Fr sm[8][32];
+  sm[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    Fr s = sm[0][lane];
+    for (int w2 = 1; w2 < nwarps; ++w2) s = add(s, sm[w2][lane]);
+    if (EPW == 2) {                                         // combine the two sub-elements of a 16-bit table
+      Fr o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = __shfl_down_sync(0xffffffffu, s.v[k], 16);
+      s = add(s, o);
+    }
+    if (lane < Q) partials[(size_t)blockIdx.x * Q + lane] = s;
+  }
+}
+__global__ void k_colsum(const Fr* __restrict__ partials, unsigned nparts, int Q, Fr* __restrict__ out) {
+  int b = threadIdx.x;
+  if (b >= Q) return;
+  Fr s = Fr::zero();
+  for (unsigned g = 0; g < nparts; ++g) s = add(s, partials[(size_t)g * Q + b]);
+  out[b] = s;
+}
+
+template <int Q, class T>
+static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, const Fr* erec,
+                                  Fr* proof_sc, Fr* proof_rec, cudaStream_t st) {
+  using PL = PackLayout<Q>;
+  const size_t k = L + PL::LOGQ;
+  int rc;
+  Scratch ud, vd, lut, ehi, a3, parts, rparts;
+  if ((rc = ud.alloc(sizeof(Fr) * k, st))) return rc;
+  if ((rc = vd.alloc(sizeof(Fr) * k, st))) return rc;
+  ZK_CUDA(cudaMemcpyAsync(ud.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  ZK_CUDA(cudaMemcpyAsync(vd.p, v_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  if ((rc = lut.alloc(sizeof(Fr) * PL::TOTAL, st))) return rc;
+  ZK_LAUNCH(k_bin_luts<Q><<<1, 256, 0, st>>>(ud.as<Fr>(), vd.as<Fr>(), lut.as<Fr>()));
+  if ((rc = ehi.alloc(sizeof(Fr) * n, st))) return rc;
+  if ((rc = build_eq_table(ud.as<Fr>() + PL::LOGQ, u_host + PL::LOGQ, (int)L, 0, ehi.as<Fr>(), st))) return rc;
+  if ((rc = a3.alloc(sizeof(Fr) * n * PL::N2, st))) return rc;
+  unsigned grid = (unsigned)num_sms();
+  if ((size_t)grid * 256 > n) grid = div_up(n, 256);
+  if ((rc = parts.alloc(sizeof(Fr) * 7 * grid, st))) return rc;
+  static bool attr_set = false;
+  size_t smem = sizeof(Fr) * PL::TOTAL;
+  if (!attr_set || true) {
+    ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 256, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), a3.as<Fr>(), parts.as<Fr>()));
+  ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, proof_sc));
+  // rounds 3.. on the folded table: binary_sumcheck(a3, u[3:], v[3:]) has exactly the remaining rounds and the final a(0)
+  if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n * PL::N2, u_host + 3, v_host + 3, k - 3, reinterpret_cast<zkdl_fr_t*>(proof_sc + 9), st))) return rc;
+  // partial_me(u_recover, Q)
+  unsigned rgrid = (unsigned)num_sms() * 2;
+  if ((size_t)rgrid * 8 > n) rgrid = div_up(n, 8);
+  if ((rc = rparts.alloc(sizeof(Fr) * Q * rgrid, st))) return rc;
+  ZK_LAUNCH(k_packed_recover<Q, T><<<rgrid, 256, 0, st>>>(packed, n, erec, rparts.as<Fr>()));
+  ZK_LAUNCH(k_colsum<<<1, 32, 0, st>>>(rparts.as<Fr>(), rgrid, Q, proof_rec));
+  return ZK_OK;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const uint32_t* mag_packed, const uint16_t* rem_packed, size_t n,
+                             const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
+                             const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
+                             zkdl_fr_t* proof_fr, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ZK_REQUIRE(X && sign && mag_packed && rem_packed && proof_fr, ZK_ERR_ARG, "null argument");
+  size_t L = 0; while (((size_t)1 << L) < n) ++L;
+  ZK_REQUIRE(((size_t)1 << L) == n && L >= 1 && L < 27, ZK_ERR_DIM, "Incompatible dimensions");
+  int rc;
+  Scratch urd, erec;
+  if ((rc = urd.alloc(sizeof(Fr) * L, st))) return rc;
+  ZK_CUDA(cudaMemcpyAsync(urd.p, u_rec_host, sizeof(Fr) * L, cudaMemcpyHostToDevice, st));
+  if ((rc = erec.alloc(sizeof(Fr) * n, st))) return rc;
+  if ((rc = build_eq_table(urd.as<Fr>(), u_rec_host, (int)L, 0, erec.as<Fr>(), st))) return rc;
+  Fr* p = reinterpret_cast<Fr*>(proof_fr);
+  Fr* p_mag_sc = p;                       p += 3 * (L + 5) + 1;
+  Fr* p_mag_rec = p;                      p += 32;
+  Fr* p_rem_sc = p;                       p += 3 * (L + 4) + 1;
+  Fr* p_rem_rec = p;                      p += 16;
+  if ((rc = packed_bin_and_recover<32, uint32_t>(mag_packed, n, L, u_z_host, v_z_host, erec.as<Fr>(), p_mag_sc, p_mag_rec, st))) return rc;
+  if ((rc = packed_bin_and_recover<16, uint16_t>(rem_packed, n, L, u_r_host, v_r_host, erec.as<Fr>(), p_rem_sc, p_rem_rec, st))) return rc;
+  return zkdl_hp_sumcheck(X, sign, n, u_hp_host, v_hp_host, L, reinterpret_cast<zkdl_fr_t*>(p), stream);      // zkrelu.cu:99
+}
+
+}  // extern "C"

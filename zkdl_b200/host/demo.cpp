@@ -52,6 +52,7 @@ static vector<zkFC> load_model(const string& model_path, vector<Commitment>& gen
 int main(int argc, char* argv[]) {
   if (argc < 3) { cerr << "usage: demo <traced_model.pt> <sample_input.pt>" << endl; return 2; }
   if (const char* s = getenv("ZKDL_SEED")) set_challenge_seed((uint32_t)atoi(s));
+  zkReLU::materialize_tables = false;        // prove() works from the packed auxiliary input
   vector<Commitment> generators; generators.reserve(64);
   vector<zkFC> fcs = load_model(argv[1], generators);
   vector<zkReLU> relus(fcs.size() - 1);

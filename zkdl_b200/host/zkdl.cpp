@@ -355,15 +355,24 @@ void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) c
 }
 
 // ------------------------------------------------------------------------------------------------ zkReLU
+bool zkReLU::materialize_tables = true;
 void zkReLU::reset_ptrs(uint size) {                                                                                    // zkrelu.cu:53-62
-  delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr;
-  sign_ptr = new FrTensor(size); mag_bin_ptr = new FrTensor(size * 32); rem_bin_ptr = new FrTensor(size * 16);
+  delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; mag_bin_ptr = rem_bin_ptr = nullptr;
+  cudaFree(mag_packed_); cudaFree(rem_packed_);
+  sign_ptr = new FrTensor(size);
+  mag_packed_ = dev_alloc<uint32_t>(size); rem_packed_ = dev_alloc<uint16_t>(size); n_ = size;
+  if (materialize_tables) { mag_bin_ptr = new FrTensor(size * 32); rem_bin_ptr = new FrTensor(size * 16); }
 }
-zkReLU::~zkReLU() { delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; sign_ptr = mag_bin_ptr = rem_bin_ptr = nullptr; }
+zkReLU::~zkReLU() {
+  delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; sign_ptr = mag_bin_ptr = rem_bin_ptr = nullptr;
+  cudaFree(mag_packed_); cudaFree(rem_packed_); mag_packed_ = nullptr; rem_packed_ = nullptr;
+}
 FrTensor zkReLU::operator()(const FrTensor& X) {                                                                        // zkrelu.cu:44-51
   reset_ptrs(X.size);
   FrTensor out(X.size);
-  check(zkdl_relu(X.gpu_data, out.gpu_data, sign_ptr->gpu_data, mag_bin_ptr->gpu_data, rem_bin_ptr->gpu_data, X.size, nullptr, 0)); sync();
+  check(zkdl_relu_packed(X.gpu_data, out.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, nullptr, 0));
+  if (materialize_tables) check(zkdl_relu_expand(mag_packed_, rem_packed_, mag_bin_ptr->gpu_data, rem_bin_ptr->gpu_data, X.size, 0));
+  sync();
   return out;
 }
 void zkReLU::prove(const FrTensor& X, const FrTensor& Z) {                                                              // zkrelu.cu:79-100
@@ -373,8 +382,8 @@ void zkReLU::prove(const FrTensor& X, const FrTensor& Z) {                      
   auto u_z = random_vec(L + 5), v_z = random_vec(L + 5), u_r = random_vec(L + 4), v_r = random_vec(L + 4), u_rec = random_vec(L);
   auto u_hp = random_vec(L), v_hp = random_vec(L);
   FrTensor p((uint)zkdl_zkrelu_proof_size(X.size));
-  check(zkdl_zkrelu_prove(X.gpu_data, sign_ptr->gpu_data, mag_bin_ptr->gpu_data, rem_bin_ptr->gpu_data, X.size, u_z.data(), v_z.data(), u_r.data(),
-                          v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), p.gpu_data, 0));
+  check(zkdl_zkrelu_prove_packed(X.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, u_z.data(), v_z.data(), u_r.data(),
+                                 v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), p.gpu_data, 0));
   sync();
   proof_ = download(p);
 }

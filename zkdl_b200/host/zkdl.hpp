@@ -208,7 +208,13 @@ class zkReLU {
   FrTensor* rem_bin_ptr = nullptr;
   void reset_ptrs(uint size);
   std::vector<Fr_t> proof_;
+  uint32_t* mag_packed_ = nullptr;               // the same auxiliary input, 48 bits per activation (device)
+  uint16_t* rem_packed_ = nullptr;
+  uint n_ = 0;
  public:
+  // true (default): operator() also materialises the reference's 0/1 Fr tables (sign/mag_bin/rem_bin pointers valid, as in
+  // the reference).  false: only the packed words are kept (1.5 KB -> 6 B per activation); prove() never needs the tables.
+  static bool materialize_tables;
   zkReLU() {}
   zkReLU(const zkReLU&) {}                       // aux tensors are per-instance state (std::vector<zkReLU> relus(n), demo.cu:103)
   FrTensor operator()(const FrTensor& X);

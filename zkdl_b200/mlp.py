@@ -64,7 +64,7 @@ class MLPProver:
             z = zk.fr_matmul(cur, L.W, B, L.I, L.O)
             self.Z.append(z)
             if i + 1 < len(self.layers):
-                a, sign, mag, rem, bad = zk.relu(z)
+                a, sign, mag, rem, bad = zk.relu_packed(z)                                  # aux kept bit-packed
                 self.A.append(a); self.aux.append((sign, mag, rem))
                 cur = a
         return self.Z[-1]
@@ -119,7 +119,7 @@ class MLPProver:
                 return
             sign, mag, rem = self.aux[i]
             with on_stream():
-                out.append(("relu", i, zk.zkrelu_prove(self.Z[i], sign, mag, rem, *ch)))
+                out.append(("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch)))
 
         fc(nl - 1)
         for i in range(nl - 2, -1, -1):
