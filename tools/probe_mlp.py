@@ -35,11 +35,10 @@ timed(lambda: zk.fr_me(P.Z[2], np.concatenate([u_out, u_bs])), "  Z(u)")
 timed(lambda: zk.open_(L.gens, L.com_table, L.W, np.concatenate([u_out, u_in])), "  open")
 timed(lambda: zk.me_open(L.gens, zk.fr_partial_me(L.W, u_in, L.gens.n), u_out), "  partial_me + me_open")
 n = B * L.O; Lg = mlp.ceil_log2(n)
-sign, mag, rem = P.aux[2]
-timed(lambda: zk.bin_sumcheck(mag, zk.random_vec(4, Lg + 5), zk.random_vec(5, Lg + 5)), "  bin_sumcheck(mag)")
-timed(lambda: zk.bin_sumcheck(rem, zk.random_vec(4, Lg + 4), zk.random_vec(5, Lg + 4)), "  bin_sumcheck(rem)")
+sign, magp, remp = P.aux[2]
+ch = [zk.random_vec(20 + i, k) for i, k in enumerate((Lg + 5, Lg + 5, Lg + 4, Lg + 4, Lg, Lg, Lg))]
+timed(lambda: zk.zkrelu_prove_packed(P.Z[2], sign, magp, remp, *ch), "  zkrelu_prove_packed")
 timed(lambda: zk.hp_sumcheck(P.Z[2], sign, zk.random_vec(4, Lg), zk.random_vec(5, Lg)), "  hp_sumcheck")
-timed(lambda: zk.fr_partial_me(mag, zk.random_vec(6, Lg), 32), "  mag.partial_me")
 timed(lambda: zk.commit(L.gens, L.W), "  commit 2048x2048")
 timed(lambda: zk.fr_matmul(P.A[1], L.W, B, L.I, L.O), "  matmul")
-timed(lambda: zk.relu(P.Z[2]), "  relu")
+timed(lambda: zk.relu_packed(P.Z[2]), "  relu_packed")

@@ -26,9 +26,8 @@ void set_last_error(const char* fmt, ...);
     if (!(cond)) { zk::set_last_error("%s:%d: %s", __FILE__, __LINE__, msg); return (code); }          \
   } while (0)
 
-// Stream-ordered scratch allocation (cudaMallocAsync on the device's default pool with the release threshold
-// raised to "never"): after warm-up the proving path performs no cudaMalloc / cudaFree and no host sync for
-// temporaries (the reference does one of each per operator, fr-tensor.cu:92-113).
+// Scratch memory from per-stream stack arenas (common.cu): after warm-up the proving path performs no cudaMalloc /
+// cudaFree and no host sync for temporaries (the reference does one of each per operator, fr-tensor.cu:92-113).
 int scratch_alloc(void** p, size_t bytes, cudaStream_t s);
 int scratch_free(void* p, cudaStream_t s);
 

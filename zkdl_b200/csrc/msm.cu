@@ -370,24 +370,19 @@ __global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ gro
 }
 
 // ------------------------------------------------------------------------------------------------ me_open scalars
-// Single CTA.  rows[(3j + {0,1,2}) * n + I] = scalars of T, T0, T1 of round j over the ORIGINAL generators;
-// rows[3k * n + I] = weights of the final folded generator; ret = final folded scalar.  See DESIGN.md §Opening.
-__global__ void __launch_bounds__(512) k_open_scalars(const Fr* __restrict__ s0, const Fr* __restrict__ u, int k, size_t n, Fr* __restrict__ rows,
-                                                      Fr* sA, Fr* sB, Fr* wA, Fr* wB, Fr* __restrict__ ret) {
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) sA[i] = s0[i];
-  if (threadIdx.x == 0) wA[0] = Fr::one();
+// k_open_fold (single CTA): the log n dependent scalar folds and generator-weight doublings of an opening, every level
+// kept: sLv[off_j + i] = s^(j)[i] (off_j = 2n - 2n/2^j), wLv[2^j - 1 + b] = w^(j)[b].  ret = the final folded scalar.
+// k_open_rows (whole grid): rows[(3j + {0,1,2}) * n + I] = scalars of T, T0, T1 of round j over the ORIGINAL generators,
+// rows[3k * n + I] = weights of the final folded generator.  See DESIGN.md §4 "An opening is one batched MSM".
+__global__ void __launch_bounds__(1024) k_open_fold(const Fr* __restrict__ s0, const Fr* __restrict__ u, int k, size_t n, Fr* sLv, Fr* wLv, Fr* __restrict__ ret) {
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) sLv[i] = s0[i];
+  if (threadIdx.x == 0) wLv[0] = Fr::one();
   __syncthreads();
-  Fr *s = sA, *sn = sB, *w = wA, *wn = wB;
+  size_t soff = 0;
   for (int j = 0; j < k; ++j) {
     size_t B = (size_t)1 << j, nj = n >> j;
-    Fr* T = rows + (size_t)(3 * j) * n; Fr* T0 = T + n; Fr* T1 = T0 + n;
-    for (size_t I = threadIdx.x; I < n; I += blockDim.x) {
-      size_t i = I >> j, b = I & (B - 1);
-      Fr wb = w[b];
-      T[I] = mul(s[i], wb);                       // raw Montgomery limbs of s times Montgomery weight = plain integer
-      if (i & 1) { T0[I] = mul(s[i - 1], wb); T1[I] = Fr::zero(); }
-      else { T1[I] = mul(s[i + 1], wb); T0[I] = Fr::zero(); }
-    }
+    const Fr* s = sLv + soff; Fr* sn = sLv + soff + nj;
+    const Fr* w = wLv + (B - 1); Fr* wn = wLv + (2 * B - 1);
     Fr uj = u[j];
     for (size_t g = threadIdx.x; g < nj / 2; g += blockDim.x) sn[g] = add(s[2 * g], mul(uj, sub(s[2 * g + 1], s[2 * g])));   // commitment.cu:55
     for (size_t b = threadIdx.x; b < B; b += blockDim.x) {    // G' = [u'] G0 + [1-u'] G1  (commitment.cu:56)
@@ -395,11 +390,24 @@ __global__ void __launch_bounds__(512) k_open_scalars(const Fr* __restrict__ s0,
       wn[b] = hi; wn[B + b] = sub(wb, hi);
     }
     __syncthreads();
-    Fr* t = s; s = sn; sn = t; t = w; w = wn; wn = t;
+    soff += nj;
   }
-  Fr* last = rows + (size_t)(3 * k) * n;
-  for (size_t I = threadIdx.x; I < n; I += blockDim.x) last[I] = from_mont(w[I]);
-  if (threadIdx.x == 0) ret[0] = s[0];
+  if (threadIdx.x == 0) ret[0] = sLv[soff];
+}
+__global__ void __launch_bounds__(256) k_open_rows(const Fr* __restrict__ sLv, const Fr* __restrict__ wLv, int k, size_t n, Fr* __restrict__ rows) {
+  const size_t total = (size_t)(k + 1) * n;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(idx / n); size_t I = idx - (size_t)j * n;
+    size_t B = (size_t)1 << j;
+    if (j == k) { rows[(size_t)(3 * k) * n + I] = from_mont(wLv[B - 1 + I]); continue; }
+    const Fr* s = sLv + (2 * n - ((2 * n) >> j));
+    size_t i = I >> j, b = I & (B - 1);
+    Fr wb = wLv[B - 1 + b];
+    Fr* T = rows + (size_t)(3 * j) * n; Fr* T0 = T + n; Fr* T1 = T0 + n;
+    T[I] = mul(s[i], wb);                         // raw Montgomery limbs of s times Montgomery weight = plain integer
+    if (i & 1) { T0[I] = mul(s[i - 1], wb); T1[I] = Fr::zero(); }
+    else { T1[I] = mul(s[i + 1], wb); T0[I] = Fr::zero(); }
+  }
 }
 
 }  // namespace zk
@@ -485,15 +493,14 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
 static int me_open_run(const zkdl_g1_table* gens, const Fr* t, size_t n, const zkdl_fr_t* u_host, size_t k, G1Jac* proof, Fr* ret, cudaStream_t st) {
   ZK_REQUIRE(n == gens->n, ZK_ERR_DIM, "Incompatible dimensions");                       // commitment.cu:64
   ZK_REQUIRE(k < 31 && n == ((size_t)1 << k), ZK_ERR_DIM, "Incompatible dimensions");    // even halving at every round (commitment.cu:46)
-  Scratch ud, rows, sA, sB, wA, wB; int rc;
+  Scratch ud, rows, sLv, wLv; int rc;
   if ((rc = ud.alloc(sizeof(Fr) * (k ? k : 1), st))) return rc;
   if (k) ZK_CUDA(cudaMemcpyAsync(ud.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
   if ((rc = rows.alloc(sizeof(Fr) * (3 * k + 1) * n, st))) return rc;
-  if ((rc = sA.alloc(sizeof(Fr) * n, st))) return rc;
-  if ((rc = sB.alloc(sizeof(Fr) * n, st))) return rc;
-  if ((rc = wA.alloc(sizeof(Fr) * n, st))) return rc;
-  if ((rc = wB.alloc(sizeof(Fr) * n, st))) return rc;
-  ZK_LAUNCH(k_open_scalars<<<1, 512, 0, st>>>(t, ud.as<Fr>(), (int)k, n, rows.as<Fr>(), sA.as<Fr>(), sB.as<Fr>(), wA.as<Fr>(), wB.as<Fr>(), ret));
+  if ((rc = sLv.alloc(sizeof(Fr) * 2 * n, st))) return rc;
+  if ((rc = wLv.alloc(sizeof(Fr) * 2 * n, st))) return rc;
+  ZK_LAUNCH(k_open_fold<<<1, 1024, 0, st>>>(t, ud.as<Fr>(), (int)k, n, sLv.as<Fr>(), wLv.as<Fr>(), ret));
+  ZK_LAUNCH(k_open_rows<<<g1_grid((k + 1) * n, 256), 256, 0, st>>>(sLv.as<Fr>(), wLv.as<Fr>(), (int)k, n, rows.as<Fr>()));
   return msm_run(gens, rows.as<Fr>(), 3 * k + 1, 0, 0, proof, st);
 }
 

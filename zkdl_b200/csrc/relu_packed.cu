@@ -161,9 +161,17 @@ __global__ void __launch_bounds__(256) k_packed_recover(const T* __restrict__ pa
   const int bit = lane % Q, sub = lane / Q;
   Fr acc = Fr::zero();
   size_t wid = (size_t)blockIdx.x * nwarps + warp, nw = (size_t)gridDim.x * nwarps;
-  for (size_t base = wid * EPW; base < n; base += nw * EPW) {
-    size_t i = base + sub;
-    if (i < n && ((packed[i] >> bit) & 1u)) acc = add(acc, e[i]);
+  constexpr int UN = 4;                                     // independent loads in flight per lane
+  for (size_t base = wid * EPW * UN; base < n; base += nw * EPW * UN) {
+    uint32_t w[UN]; Fr ev[UN];
+#pragma unroll
+    for (int r = 0; r < UN; ++r) {
+      size_t i = base + r * EPW + sub;
+      w[r] = i < n ? (uint32_t)packed[i] : 0u;
+      ev[r] = i < n ? e[i] : Fr::zero();
+    }
+#pragma unroll
+    for (int r = 0; r < UN; ++r) if ((w[r] >> bit) & 1u) acc = add(acc, ev[r]);
   }
   __shared__ Fr sm[8][32];
   sm[warp][lane] = acc;
@@ -180,12 +188,19 @@ __global__ void __launch_bounds__(256) k_packed_recover(const T* __restrict__ pa
     if (lane < Q) partials[(size_t)blockIdx.x * Q + lane] = s;
   }
 }
-__global__ void k_colsum(const Fr* __restrict__ partials, unsigned nparts, int Q, Fr* __restrict__ out) {
-  int b = threadIdx.x;
-  if (b >= Q) return;
+// out[b] = sum_g partials[g][b]; 8 row groups per column, combined through shared memory
+__global__ void __launch_bounds__(256) k_colsum(const Fr* __restrict__ partials, unsigned nparts, int Q, Fr* __restrict__ out) {
+  __shared__ Fr sm[8][32];
+  const int b = threadIdx.x & 31, grp = threadIdx.x >> 5;
   Fr s = Fr::zero();
-  for (unsigned g = 0; g < nparts; ++g) s = add(s, partials[(size_t)g * Q + b]);
-  out[b] = s;
+  if (b < Q)
+    for (unsigned g = grp; g < nparts; g += 8) s = add(s, partials[(size_t)g * Q + b]);
+  sm[grp][b] = s;
+  __syncthreads();
+  if (grp == 0 && b < Q) {
+    for (int w2 = 1; w2 < 8; ++w2) s = add(s, sm[w2][b]);
+    out[b] = s;
+  }
 }
 
 template <int Q, class T>
@@ -219,10 +234,10 @@ static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkd
   if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n * PL::N2, u_host + 3, v_host + 3, k - 3, reinterpret_cast<zkdl_fr_t*>(proof_sc + 9), st))) return rc;
   // partial_me(u_recover, Q)
   unsigned rgrid = (unsigned)num_sms() * 2;
-  if ((size_t)rgrid * 8 > n) rgrid = div_up(n, 8);
+  if ((size_t)rgrid * 8 * 4 > n) rgrid = div_up(n, 32);
   if ((rc = rparts.alloc(sizeof(Fr) * Q * rgrid, st))) return rc;
   ZK_LAUNCH(k_packed_recover<Q, T><<<rgrid, 256, 0, st>>>(packed, n, erec, rparts.as<Fr>()));
-  ZK_LAUNCH(k_colsum<<<1, 32, 0, st>>>(rparts.as<Fr>(), rgrid, Q, proof_rec));
+  ZK_LAUNCH(k_colsum<<<1, 256, 0, st>>>(rparts.as<Fr>(), rgrid, Q, proof_rec));
   return ZK_OK;
 }
 

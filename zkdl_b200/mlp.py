@@ -69,7 +69,7 @@ class MLPProver:
                 cur = a
         return self.Z[-1]
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=4):
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
         fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); challenges are drawn for
         every layer regardless, so a layer's proof does not depend on which rank produced it.
