@@ -135,8 +135,9 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- our arm
 def cpu_baseline_sample():
-    """Oracle port on the host cores: one hidden layer (2048x2048 weights, batch 256) zkFC sumcheck set + zkReLU
-    sumchecks at reduced size + an opening at |G| = 256, scaled to the whole proof by exact operation counts."""
+    """Oracle port (oracle/zkdl_oracle.c, OpenMP) on the host cores, bounded sample: one hidden layer's zkFC sumcheck set
+    at full size (2048x2048 weights, batch 256), its opening at |G| = 2048, and the zkReLU proof at n = 2^17 activations
+    (a quarter of that layer's), scaled to the 8-layer proof by table sizes."""
     import numpy as np
     from oracle import oracle as orc
     rng = np.random.default_rng(0)
@@ -146,44 +147,41 @@ def cpu_baseline_sample():
         v = rng.integers(0, lim, size=(n, 8), dtype=np.uint64).astype(np.uint32)
         v[:, 1:] = 0
         return orc.fr_mont(v)
-    # (1) Fr work: zkFC sumcheck set on I=O=1024, B=256 (1/4 of a hidden layer's W traffic)
-    I = O = 1024; B = 256
+    I = O = 2048; B = 256
     W, X = small(I * O, 1 << 13), small(B * I, 1 << 16)
-    u_bs, u_in, u_out = orc.random_vec(1, 8), orc.random_vec(2, 10), orc.random_vec(3, 10)
+    Zt = small(B * O, 1 << 30)
+    u_bs, u_in, u_out = orc.random_vec(1, 8), orc.random_vec(2, 11), orc.random_vec(3, 11)
     t0 = time.time()
     Xr = orc.fr_partial_me(X, u_bs, I); Wr = orc.fr_partial_me(W, u_out, 1); orc.ip_sumcheck(Xr, Wr, u_in)
+    orc.fr_me(Zt, np.concatenate([u_out, u_bs]))
     t_fc = time.time() - t0
-    # (2) zkReLU sumchecks at n = 2^12 activations (mag_bin 2^17 cells)
-    n = 1 << 12
+    ng = 2048
+    G = orc.g1_mul(orc.g1_generator(), orc.random_vec(11, ng), fast=True)
+    com = orc.g1_mul(orc.g1_generator(), orc.random_vec(12, ng), fast=True)
+    t0 = time.time()
+    orc.open_(W, G, com, np.concatenate([u_out, u_in]))            # the reference's ladders (g1-tensor.cu:422-430), all cores
+    t_open = time.time() - t0
+    n = 1 << 17; L = 17
     Zp = orc.fr_from_ints([int(v) for v in rng.integers(-(1 << 40), 1 << 40, size=n)])
     A, sign, mag, rem, _ = orc.relu(Zp)
-    L = 12
     t0 = time.time()
-    orc.bin_sumcheck(mag, orc.random_vec(4, L + 5), orc.random_vec(5, L + 5)); orc.fr_partial_me(mag, orc.random_vec(6, L), 32)
-    orc.bin_sumcheck(rem, orc.random_vec(7, L + 4), orc.random_vec(8, L + 4)); orc.fr_partial_me(rem, orc.random_vec(6, L), 16)
-    orc.hp_sumcheck(Zp, sign, orc.random_vec(9, L), orc.random_vec(10, L))
+    orc.zkrelu_prove(Zp, sign, mag, rem, orc.random_vec(4, L + 5), orc.random_vec(5, L + 5), orc.random_vec(7, L + 4), orc.random_vec(8, L + 4),
+                     orc.random_vec(6, L), orc.random_vec(9, L), orc.random_vec(10, L))
     t_relu = time.time() - t0
-    # (3) opening: me_open at |G| = 128 with the reference's ladders
-    ng = 128
-    G = orc.g1_mul(orc.g1_generator(), orc.random_vec(11, ng), fast=True)
-    t0 = time.time()
-    orc.me_open(orc.random_vec(12, ng), G, orc.random_vec(13, 7))
-    t_open = time.time() - t0
-    # scale to the demo proof: W cells 2^20 -> sum over layers of I*O (padded); relu cells ~ n log n; open ~ |G|
-    w_cells = 2 ** 20 + 2 ** 21 + 5 * 2 ** 22 + 2 ** 21
-    relu_scale = sum((256 * o) * (1 + 0.0) for o in (1024, 2048, 2048, 2048, 2048, 2048, 2048)) / n * (19 + 5) / (12 + 5)
+    fc_scale = (2 ** 20 + 2 ** 21 + 5 * 2 ** 22 + 2 ** 21) / 2 ** 22
+    relu_scale = (2 ** 18 * 23 + 6 * 2 ** 19 * 24) / (n * (L + 5))
     open_scale = (1024 + 7 * 2048) / ng
-    est = t_fc * (w_cells / 2 ** 20) + t_relu * relu_scale + t_open * open_scale
+    est = t_fc * fc_scale + t_relu * relu_scale + t_open * open_scale
     return {"value": est, "unit": "s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"oracle port (C, OpenMP): zkFC sumcheck set 1024x1024xB256 {t_fc:.2f}s, zkReLU sumchecks n=2^12 {t_relu:.2f}s, "
-                      f"me_open |G|=128 {t_open:.2f}s ({time.time() - t_all:.1f}s of CPU work), scaled to the 8-layer proof by table sizes "
-                      "(the reference's O(n log n) ReLU recursion and 255-bit ladders are what the port executes)"}
+            "sample": f"oracle port (C, OpenMP, {orc.num_threads()} threads): zkFC sumcheck set 2048x2048xB256 {t_fc:.2f}s (x{fc_scale:.2f}), "
+                      f"Commitment::open |G|=2048 {t_open:.2f}s (x{open_scale:.1f}), zkReLU::prove n=2^17 {t_relu:.2f}s (x{relu_scale:.1f}); "
+                      f"{time.time() - t_all:.1f}s of CPU work, scaled to the 8-layer batch-256 proof by table sizes"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -194,7 +192,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from zkdl_b200 import capi as zk, mlp
+    from zkdl_b200 import capi as zk, mlp, parallel
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a GPU: the CUDA extension is the product, there is no CPU fallback"
@@ -212,8 +210,7 @@ def main():
     x_host = x.cpu().pin_memory()
     P.forward(x)
     nl = len(P.layers)
-    my_fc = [i for i in range(nl) if i % world == rank]
-    my_relu = [i for i in range(nl - 1) if i % world == rank]
+    my_fc, my_relu = parallel.partition_layers(nl, world, rank)
 
     def barrier():
         if world > 1:
@@ -224,12 +221,9 @@ def main():
         parts = P.prove(seed=seed, fc_layers=my_fc, relu_layers=my_relu)
         flat = torch.cat([t.reshape(-1) for p in parts for t in p[2:]])
         if world > 1:                                   # proof elements of the other ranks' layers -> rank 0
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"))
-            mx = int(max(s.item() for s in sizes))
-            buf = torch.zeros(mx, dtype=flat.dtype, device="cuda"); buf[: flat.numel()] = flat
-            outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-            dist.gather(buf, outs, dst=0)
+            parts = parallel.gather_proof(flat, world, rank, "cuda")
+            if rank == 0:
+                flat = torch.cat(parts)
         return flat
 
     def e2e_step(seed):

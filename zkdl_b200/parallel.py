@@ -1,0 +1,30 @@
+"""Multi-GPU plumbing of the layer-parallel prover: which rank proves which layer, and how the proof
+elements reach rank 0.  There is no data-path collective: every layer's zkFC / zkReLU proof is independent once the
+forward pass has run, so ranks only exchange finished proof elements (a padded gather, ~100 KB).
+Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+import torch
+import torch.distributed as dist
+
+
+def partition_layers(n_layers, world, rank):
+    """Layers (fc i, relu i) owned by `rank`: round-robin, so that the 8 fc + 7 relu proofs of the demo MLP spread
+    evenly.  Returns (fc_layers, relu_layers)."""
+    fc = [i for i in range(n_layers) if i % world == rank]
+    relu = [i for i in range(n_layers - 1) if i % world == rank]
+    return fc, relu
+
+
+def gather_proof(flat, world, rank, device):
+    """Gathers each rank's flat proof tensor on rank 0.  Returns the list of per-rank tensors on rank 0, None elsewhere."""
+    if world == 1:
+        return [flat]
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([flat.numel()], dtype=torch.int64, device=device))
+    mx = int(max(int(s.item()) for s in sizes))
+    buf = torch.zeros(mx, dtype=flat.dtype, device=device)
+    buf[: flat.numel()] = flat
+    outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+    dist.gather(buf, outs, dst=0)
+    if rank != 0:
+        return None
+    return [o[: int(s.item())] for o, s in zip(outs, sizes)]
