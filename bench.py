@@ -199,6 +199,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU: the CUDA extension is the product, there is no CPU fallback"
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/zkdl_nccl_%h_%p.log")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     zk.lib()
 

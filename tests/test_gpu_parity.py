@@ -113,6 +113,14 @@ def test_quantise_matmul_relu(zk):
     A, B = small_fr(24 * 40), small_fr(40 * 33)
     got = zk.to_host(zk.fr_matmul(zk.to_device(A), zk.to_device(B), 24, 40, 33))
     assert eq(got, orc.fr_matmul(A, B, 24, 40, 33))
+    # operands outside the small-integer range take the generic Fr path; mixed and boundary cases
+    A2, B2 = rand_fr(5 * 7), rand_fr(7 * 3)
+    assert eq(zk.to_host(zk.fr_matmul(zk.to_device(A2), zk.to_device(B2), 5, 7, 3)), orc.fr_matmul(A2, B2, 5, 7, 3))
+    lim = [(1 << 31) - 1, -(1 << 31), 1 << 31, -(1 << 31) - 1, 0, 1, -1]
+    A3 = orc.fr_from_ints([lim[i % 7] for i in range(70 * 65)]); B3 = orc.fr_from_ints([lim[(3 * i + 1) % 5] for i in range(65 * 66)])
+    assert eq(zk.to_host(zk.fr_matmul(zk.to_device(A3), zk.to_device(B3), 70, 65, 66)), orc.fr_matmul(A3, B3, 70, 65, 66))
+    A4 = orc.fr_from_ints([lim[i % 2] for i in range(130 * 100)]); B4 = orc.fr_from_ints([lim[(i + 1) % 2] for i in range(100 * 67)])
+    assert eq(zk.to_host(zk.fr_matmul(zk.to_device(A4), zk.to_device(B4), 130, 100, 67)), orc.fr_matmul(A4, B4, 130, 100, 67))
     xs = [int(v) for v in rng.integers(-(1 << 46), 1 << 46, size=3000)] + [0, 1, -1, 32767, 32768, -32768, -32769, (1 << 47) - 1, -(1 << 47), 1 << 47, -(1 << 47) - 1]
     X = orc.fr_from_ints(xs, mont=True)
     Z, sign, mag, rem, bad = zk.relu(zk.to_device(X))

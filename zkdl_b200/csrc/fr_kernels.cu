@@ -250,7 +250,8 @@ __global__ void __launch_bounds__(THREADS) k_float_to_fr(const float* __restrict
 static constexpr int MM_TILE = 16;
 // C = A * B over Fr; 16x16 output tile per CTA, K-tiles staged through shared memory.
 __global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
-                                                                 size_t rowsA, size_t colsA, size_t colsB) {
+                                                                 size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ only_if) {
+  if (only_if && *only_if == 0) return;                      // the small-integer fast path already produced C
   __shared__ Fr As[MM_TILE][MM_TILE];
   __shared__ Fr Bs[MM_TILE][MM_TILE];
   const int tx = threadIdx.x % MM_TILE, ty = threadIdx.x / MM_TILE;
@@ -265,6 +266,76 @@ __global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __res
     __syncthreads();
   }
   if (row < rowsA && col < colsB) C[row * colsB + col] = sum;
+}
+
+// ---- small-integer fast path of the forward matmul.  Quantised activations and weights are Montgomery forms of small
+// signed integers (|v| < 2^31: inputs at scale 2^16, rescaled activations are u32 magnitudes, zkrelu.cu:29).  The exact
+// integer dot product (128-bit accumulator) reduced mod p is the same field element as the Fr dot product, so the result
+// is bit-identical; ~5 integer instructions per multiply-add instead of a 136-IMAD Montgomery product.  Any operand
+// outside the range raises `flag`, and the generic Fr kernel (launched right after, exiting early otherwise) recomputes.
+__global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in, int32_t* __restrict__ out, size_t n, uint32_t* __restrict__ flag) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = from_mont(in[i]);
+    bool hi0 = (x.v[1] | x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7]) == 0;
+    int32_t r = 0;
+    if (hi0 && x.v[0] < 0x80000000u) r = (int32_t)x.v[0];
+    else {
+      Fr m = sub(Fr::zero(), x);                              // p - x
+      bool mhi0 = (m.v[1] | m.v[2] | m.v[3] | m.v[4] | m.v[5] | m.v[6] | m.v[7]) == 0;
+      if (mhi0 && m.v[0] <= 0x80000000u) r = (int32_t)(0u - m.v[0]);
+      else atomicOr(flag, 1u);
+    }
+    out[i] = r;
+  }
+}
+static constexpr int IM_T = 64, IM_K = 32;                    // 64x64 outputs per CTA, 4x4 per thread, K tiles of 32
+__global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
+                                                    size_t rowsA, size_t colsA, size_t colsB) {
+  __shared__ __align__(16) int32_t As[IM_K][IM_T + 4];        // [k][row], padded: 16-byte aligned rows, 4-way store conflicts at most
+  __shared__ __align__(16) int32_t Ws[IM_K][IM_T];            // [k][col]
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const size_t row0 = (size_t)blockIdx.y * IM_T, col0 = (size_t)blockIdx.x * IM_T;
+  __int128 acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+  for (size_t k0 = 0; k0 < colsA; k0 += IM_K) {
+    for (int e = threadIdx.x; e < IM_T * IM_K; e += 256) {
+      int r = e / IM_K, k = e % IM_K;                          // A: consecutive threads read consecutive k
+      size_t gr = row0 + r, gk = k0 + k;
+      As[k][r] = (gr < rowsA && gk < colsA) ? A[gr * colsA + gk] : 0;
+      int kk = e / IM_T, c = e % IM_T;                         // W: consecutive threads read consecutive columns
+      size_t gk2 = k0 + kk, gc = col0 + c;
+      Ws[kk][c] = (gk2 < colsA && gc < colsB) ? W[gk2 * colsB + gc] : 0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < IM_K; ++k) {
+      const int4 av = *reinterpret_cast<const int4*>(&As[k][ty * 4]);
+      const int4 wv = *reinterpret_cast<const int4*>(&Ws[k][tx * 4]);
+      const int32_t a[4] = {av.x, av.y, av.z, av.w}, w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += (__int128)((int64_t)a[i] * (int64_t)w[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      size_t gr = row0 + ty * 4 + i, gc = col0 + tx * 4 + j;
+      if (gr >= rowsA || gc >= colsB) continue;
+      __int128 v = acc[i][j];
+      bool negative = v < 0;
+      unsigned __int128 m = negative ? (unsigned __int128)(-v) : (unsigned __int128)v;
+      Fr r = Fr::zero();
+      r.v[0] = (uint32_t)m; r.v[1] = (uint32_t)(m >> 32); r.v[2] = (uint32_t)(m >> 64); r.v[3] = (uint32_t)(m >> 96);
+      r = to_mont(r);
+      C[gr * colsB + gc] = negative ? neg(r) : r;
+    }
 }
 
 // relu: Z, sign and the packed decomposition (q: u32 rescaled magnitude, r: u16 = rem_mag | rem_sign << 15)
@@ -505,8 +576,18 @@ int zkdl_float_to_fr(const float* fs, zkdl_fr_t* out, uint32_t rows_in, uint32_t
 
 int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t rowsA, size_t colsA, size_t colsB, void* stream) {
   if (rowsA == 0 || colsB == 0) return ZK_OK;
+  cudaStream_t st = S(stream);
+  Scratch ai, wi, flag; int rc;
+  if ((rc = ai.alloc(sizeof(int32_t) * rowsA * colsA, st))) return rc;
+  if ((rc = wi.alloc(sizeof(int32_t) * colsA * colsB, st))) return rc;
+  if ((rc = flag.alloc(sizeof(uint32_t), st))) return rc;
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), st));
+  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(F(A), ai.as<int32_t>(), rowsA * colsA, flag.as<uint32_t>()));
+  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(colsA * colsB, THREADS), THREADS, 0, st>>>(F(B), wi.as<int32_t>(), colsA * colsB, flag.as<uint32_t>()));
+  dim3 igrid(div_up(colsB, IM_T), div_up(rowsA, IM_T));
+  ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), wi.as<int32_t>(), F(C), rowsA, colsA, colsB));
   dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
-  ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, S(stream)>>>(F(A), F(B), F(C), rowsA, colsA, colsB));
+  ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, st>>>(F(A), F(B), F(C), rowsA, colsA, colsB, flag.as<uint32_t>()));
   return ZK_OK;
 }
 
