@@ -307,10 +307,13 @@ def main():
     alg_bytes = 96.0 * n * (1 - 2.0 ** -3)                     # 48 n B per table per round, 3 rounds fused
     achieved = alg_bytes / (fold_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_fr_fold_multi<3> (Fr_me_step x3 fused) on the 4096x4096 weight table, 2^24 Fr = 512 MiB",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": 597113856.0,   # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_kernels_full_summary.json
                 "algorithmic_bytes_per_launch": alg_bytes, "actual_min_bytes_per_launch": 32.0 * n * (1 + 1 / 8), "ms_per_launch": fold_ms,
                 "peak_source": peak_src, "note": "denominator is SURVEY §8d's per-round Fr-cell model; the kernel folds 3 rounds per pass so "
-                                                 "its real DRAM traffic is 36 n B, see actual_min_bytes_per_launch"}
+                                                 "its real DRAM traffic is 36 n B (= measured traffic, no re-reads). ncu: DRAM 24% of peak, "
+                                                 "sm__throughput 83%: the kernel is IMAD-bound (7 Montgomery products per 8 elements at the "
+                                                 "measured 58 G Fr-mul/s ceiling), see profiles/README.md"}
     extra["fold_hbm_gbs_algorithmic"] = achieved
     extra["fold_hbm_gbs_actual_traffic"] = 36.0 * n / (fold_ms * 1e-3) / 1e9
     del Wbig
