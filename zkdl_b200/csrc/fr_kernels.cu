@@ -133,13 +133,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_eq_small(const Fr* __restrict_
     __syncthreads();
   }
 }
-__global__ void __launch_bounds__(THREADS) k_eq_level(Fr* __restrict__ E, Fr qj, size_t half, int rev) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < half; i += (size_t)gridDim.x * blockDim.x) {
-    Fr e = E[i];
-    Fr hi = mul(e, qj), lo = sub(e, hi);
-    if (rev) { E[i] = hi; E[i + half] = lo; } else { E[i] = lo; E[i + half] = hi; }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ sumcheck rounds
 enum { SC_IP = 0, SC_HP = 1, SC_BIN = 2 };
@@ -182,16 +175,41 @@ __device__ __forceinline__ void sc_round_items(const Fr* __restrict__ a, const F
   }
 }
 
+__device__ __forceinline__ Fr ldcg_fr(const Fr* p) {          // L2 load (other CTAs' partials: L1 is not coherent)
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  Fr r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+// One sumcheck round over the whole table.  Per-CTA partial sums go to `partials`; the last CTA to finish (ticket from
+// `counter`, which it resets) adds them up and writes the round's three proof elements: no separate reduction launch.
 template <int KIND>
 __global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
                                                       const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x, size_t in_size, size_t out_size,
-                                                      size_t H, Fr* __restrict__ partials) {
+                                                      size_t H, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof3) {
   __shared__ Fr sm[3 * 32];
+  __shared__ bool is_last;
   Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
   sc_round_items<KIND>(a, b, a_out, b_out, e_in, e_out, x, in_size, out_size, H,
                        blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, acc);
   block_reduce_fr<3>(acc, sm);
-  if (threadIdx.x == 0) { partials[blockIdx.x * 3 + 0] = acc[0]; partials[blockIdx.x * 3 + 1] = acc[1]; partials[blockIdx.x * 3 + 2] = acc[2]; }
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0]; partials[blockIdx.x * 3 + 1] = acc[1]; partials[blockIdx.x * 3 + 2] = acc[2];
+    __threadfence();
+    is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  acc[0] = acc[1] = acc[2] = Fr::zero();
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    acc[0] = add(acc[0], ldcg_fr(partials + (size_t)i * 3));
+    acc[1] = add(acc[1], ldcg_fr(partials + (size_t)i * 3 + 1));
+    acc[2] = add(acc[2], ldcg_fr(partials + (size_t)i * 3 + 2));
+  }
+  __syncthreads();
+  block_reduce_fr<3>(acc, sm);
+  if (threadIdx.x == 0) { proof3[0] = acc[0]; proof3[1] = acc[1]; proof3[2] = acc[2]; *counter = 0; }
 }
 
 // All remaining rounds in one CTA.  bufs: a0/a1 (and b0/b1) ping-pong, e0/e1 ping-pong.  xs = fold challenges for the
@@ -369,13 +387,24 @@ static int upload_frs(const zkdl_fr_t* host, size_t k, Scratch& buf, cudaStream_
 }
 
 // builds E over q[0..t-1] (device) into E (2^t entries)
+// E[i] = lo[i & (2^tl - 1)] * hi[i >> tl]: eq over t variables as the outer product of two half-size eq tables
+__global__ void __launch_bounds__(THREADS) k_eq_outer(const Fr* __restrict__ lo, const Fr* __restrict__ hi, int tl, size_t n, Fr* __restrict__ E) {
+  const size_t mask = ((size_t)1 << tl) - 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) E[i] = mul(lo[i & mask], hi[i >> tl]);
+}
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st) {
-  int small = t < 11 ? t : 11;
-  ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, small, rev, E));
-  for (int j = small; j < t; ++j) {
-    size_t half = (size_t)1 << j;
-    ZK_LAUNCH(k_eq_level<<<stream_grid(half, THREADS), THREADS, 0, st>>>(E, host_fr(q_host + j), half, rev));
-  }
+  (void)q_host;
+  if (t <= 11) { ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, t, rev, E)); return ZK_OK; }
+  // eq(q, i) factors over the low tl and high t - tl variables: two small single-CTA tables + one product pass
+  // (3 launches instead of one per level).  Up to 22 variables both halves fit k_eq_small; beyond that recurse on hi.
+  int tl = 11, th = t - tl;
+  Scratch lo, hi; int rc;
+  if ((rc = lo.alloc(sizeof(Fr) * ((size_t)1 << tl), st))) return rc;
+  if ((rc = hi.alloc(sizeof(Fr) * ((size_t)1 << th), st))) return rc;
+  ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, tl, rev, lo.as<Fr>()));
+  if ((rc = build_eq_table(q_dev + tl, nullptr, th, rev, hi.as<Fr>(), st))) return rc;
+  size_t n = (size_t)1 << t;
+  ZK_LAUNCH(k_eq_outer<<<stream_grid(n, THREADS), THREADS, 0, st>>>(lo.as<Fr>(), hi.as<Fr>(), tl, n, E));
   return ZK_OK;
 }
 
@@ -437,8 +466,12 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   if ((rc = A0.alloc(sizeof(Fr) * half, st))) return rc;
   if ((rc = A1.alloc(sizeof(Fr) * half, st))) return rc;
   if (KIND != SC_BIN) { if ((rc = B0.alloc(sizeof(Fr) * half, st))) return rc; if ((rc = B1.alloc(sizeof(Fr) * half, st))) return rc; }
-  unsigned maxgrid = stream_grid((half + 1) / 2, THREADS);
+  size_t maxH = (half + 1) / 2; if (KIND != SC_IP && esize / 2 > maxH) maxH = esize / 2;   // HP/BIN rounds cover the whole eq table
+  unsigned maxgrid = stream_grid(maxH, THREADS);
   if ((rc = parts.alloc(sizeof(Fr) * 3 * maxgrid, st))) return rc;
+  Scratch counter;
+  if ((rc = counter.alloc(sizeof(unsigned), st))) return rc;
+  ZK_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
 
   const Fr *ca = a, *cb = b; size_t cur_n = n;
   Fr *abuf[2] = {A0.as<Fr>(), A1.as<Fr>()}, *bbuf[2] = {B0.as<Fr>(), B1.as<Fr>()};
@@ -452,8 +485,7 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
     size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
     unsigned grid = stream_grid(H, THREADS);
     ZK_LAUNCH(k_sc_round<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
-                                                         host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>()));
-    ZK_LAUNCH(k_fr_sum_final<3><<<1, TAIL_THREADS, 0, st>>>(parts.as<Fr>(), grid, proof + 3 * j));
+                                                         host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j));
     ca = abuf[which]; cb = bbuf[which]; which ^= 1; cur_n = out_size;
     if (fold_e) { ewhich ^= 1; esize /= 2; }
   }

@@ -16,6 +16,7 @@
 // me_open's log|G| dependent folding rounds are re-expressed as 3*log|G|+1 independent MSMs over the ORIGINAL
 // generators (k_open_scalars computes the per-round scalars), so a whole opening is ONE batched MSM.
 #include <atomic>
+#include <stdlib.h>
 #include "common.cuh"
 #include "g1_device.cuh"
 #include "../../include/zkdl_b200.h"
@@ -422,6 +423,7 @@ struct zkdl_g1_table {
 namespace zk {
 
 static int pick_c(const zkdl_g1_table* t, size_t m) {
+  if (const char* e = getenv("ZKDL_MSM_C")) { int c = atoi(e); if (c >= 4 && c <= 16) return c; }   // tuning knob
   if (t->full) return m >= 64 ? 8 : 12;
   int lg = 0; while (((size_t)1 << (lg + 1)) <= t->n) ++lg;
   int c = lg - 5; if (c < 4) c = 4; if (c > 16) c = 16;
@@ -516,7 +518,7 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   if (khi > 0) ZK_REQUIRE(!(ncom <= ((size_t)1 << (khi - 1)) || ncom > ((size_t)1 << khi)), ZK_ERR_DIM, "Incompatible dimensions");
   // com(u_hi) and the opening proper are independent: fork the commitment-vector evaluation onto a side stream so its
   // latency-bound bucket reduction overlaps the opening MSM (joined before returning).
-  static cudaStream_t side = nullptr; static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static thread_local cudaStream_t side = nullptr; static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // per host thread
   if (!side) {
     ZK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
     ZK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));

@@ -69,68 +69,85 @@ class MLPProver:
                 cur = a
         return self.Z[-1]
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8):
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=True):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
         fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); challenges are drawn for
         every layer regardless, so a layer's proof does not depend on which rank produced it.
         Every layer's proof is independent of the others (all randomness is fresh), so the per-layer
-        proofs are issued round-robin on `streams` CUDA streams: the latency-bound bucket reductions of one layer's
-        opening overlap the bandwidth-bound sumcheck passes of another."""
+        proofs are issued on `streams` CUDA streams: the latency-bound bucket reductions of one layer's opening overlap
+        the bandwidth-bound sumcheck passes of another.  With threads=True each stream is fed by its own host thread
+        (ctypes releases the GIL, the library is thread-safe), so the ~1200 kernel launches of a proof are issued in
+        parallel instead of from one core."""
         import torch
         ctr = [seed]
-        main = torch.cuda.current_stream()
-        if streams > 1:
-            if len(getattr(self, "_streams", [])) != streams:
-                self._streams = [torch.cuda.Stream() for _ in range(streams)]
-            start = torch.cuda.Event(); start.record(main)
-            for s_ in self._streams:
-                s_.wait_event(start)
-        slot = [0]
-
-        def on_stream():
-            if streams <= 1:
-                return torch.cuda.stream(main)
-            st = self._streams[slot[0] % streams]; slot[0] += 1
-            return torch.cuda.stream(st)
 
         def rv(k):
             ctr[0] += 1
             return zk.random_vec(ctr[0], k)
 
         B, kb = self.B, ceil_log2(self.B)
-        out = []
         nl = len(self.layers)
+        tasks = []                                   # (kind, layer, challenges) in the reference's order
 
         def fc(i):
             L = self.layers[i]
-            Xin = self.A[i - 1] if i > 0 else self.X
-            u_bs, u_in, u_out = rv(kb), rv(ceil_log2(L.I)), rv(ceil_log2(L.O))               # zkfc.cu:135-137
-            if fc_layers is not None and i not in fc_layers:
-                return
-            with on_stream():
-                out.append(("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, u_bs, u_in, u_out))
+            ch = (rv(kb), rv(ceil_log2(L.I)), rv(ceil_log2(L.O)))                             # zkfc.cu:135-137
+            if fc_layers is None or i in fc_layers:
+                tasks.append(("fc", i, ch))
 
         def relu(i):
-            n = B * self.layers[i].O
-            Lg = ceil_log2(n)
+            Lg = ceil_log2(B * self.layers[i].O)
             ch = [rv(Lg + 5), rv(Lg + 5), rv(Lg + 4), rv(Lg + 4), rv(Lg)]                    # zkrelu.cu:85-89
             ch += [rv(Lg), rv(Lg)]                                                           # zkrelu.cu:97-98
-            if relu_layers is not None and i not in relu_layers:
-                return
-            sign, mag, rem = self.aux[i]
-            with on_stream():
-                out.append(("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch)))
+            if relu_layers is None or i in relu_layers:
+                tasks.append(("relu", i, ch))
 
         fc(nl - 1)
         for i in range(nl - 2, -1, -1):
             relu(i)
             fc(i)
-        if streams > 1:
-            for s_ in self._streams:
-                ev = torch.cuda.Event(); ev.record(s_); main.wait_event(ev)
-            for part in out:                       # proof tensors were allocated on side streams
+
+        def run(task):
+            kind, i, ch = task
+            L = self.layers[i]
+            if kind == "fc":
+                Xin = self.A[i - 1] if i > 0 else self.X
+                return ("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, *ch)
+            sign, mag, rem = self.aux[i]
+            return ("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch))
+
+        main = torch.cuda.current_stream()
+        if streams <= 1 or len(tasks) <= 1:
+            return [run(t) for t in tasks]
+        if len(getattr(self, "_streams", [])) != streams:
+            self._streams = [torch.cuda.Stream() for _ in range(streams)]
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=streams)
+        start = torch.cuda.Event(); start.record(main)
+        dev = torch.cuda.current_device()
+
+        def worker(slot):
+            torch.cuda.set_device(dev)
+            st = self._streams[slot]
+            st.wait_event(start)
+            res = []
+            with torch.cuda.stream(st):
+                for j in range(slot, len(tasks), streams):
+                    res.append((j, run(tasks[j])))
+            ev = torch.cuda.Event(); ev.record(st)
+            return res, ev
+
+        if threads:
+            outs = list(self._pool.map(worker, range(streams)))
+        else:
+            outs = [worker(s_) for s_ in range(streams)]
+        out = [None] * len(tasks)
+        for res, ev in outs:
+            main.wait_event(ev)
+            for j, part in res:
+                out[j] = part
                 for t in part[2:]:
-                    t.record_stream(main)
+                    t.record_stream(main)            # proof tensors were allocated on side streams
         return out
 
 
