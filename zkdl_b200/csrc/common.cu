@@ -36,13 +36,6 @@ int scratch_alloc(void** p, size_t bytes, cudaStream_t s) {
   int dev = 0; ZK_CUDA(cudaGetDevice(&dev));
   Arena& a = g_arenas[{dev, s}];
   bytes = (bytes + ALIGN - 1) / ALIGN * ALIGN;
-  if (a.stack.empty() && a.blocks.size() > 1) {           // consolidate the warm-up blocks into one
-    size_t total = 0;
-    for (auto& b : a.blocks) { total += b.cap; cudaFree(b.base); }
-    a.blocks.clear();
-    char* base = nullptr; ZK_CUDA(cudaMalloc((void**)&base, total));
-    a.blocks.push_back({base, total, 0});
-  }
   if (a.blocks.empty() || a.blocks.back().top + bytes > a.blocks.back().cap) {
     size_t cap = a.blocks.empty() ? (size_t)64 << 20 : a.blocks.back().cap * 2;
     if (cap < bytes) cap = bytes;
@@ -66,6 +59,14 @@ int scratch_free(void* p, cudaStream_t s) {
   while (!a.stack.empty() && !a.stack.back().live) {       // pop every released allocation on top of the stack
     a.blocks[a.stack.back().block].top = a.stack.back().off;
     a.stack.pop_back();
+  }
+  if (a.stack.empty() && a.blocks.size() > 1) {           // end of a warm-up call: consolidate its blocks into one
+    size_t total = 0;
+    cudaStreamSynchronize(s);                             // the call's kernels may still be using the blocks
+    for (auto& b : a.blocks) { total += b.cap; cudaFree(b.base); }
+    a.blocks.clear();
+    char* base = nullptr; ZK_CUDA(cudaMalloc((void**)&base, total));
+    a.blocks.push_back({base, total, 0});
   }
   return ZK_OK;
 }
