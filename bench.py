@@ -219,11 +219,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    proof_sizes = []
+
     def prove_step(seed):
         parts = P.prove(seed=seed, fc_layers=my_fc, relu_layers=my_relu)
         flat = torch.cat([t.reshape(-1) for p in parts for t in p[2:]])
         if world > 1:                                   # proof elements of the other ranks' layers -> rank 0
-            parts = parallel.gather_proof(flat, world, rank, "cuda")
+            if not proof_sizes:                         # per-rank sizes depend only on the model shape: exchange once
+                szs = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+                dist.all_gather(szs, torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"))
+                proof_sizes.extend(int(s_.item()) for s_ in szs)
+            parts = parallel.gather_proof(flat, world, rank, "cuda", sizes=proof_sizes)
             if rank == 0:
                 flat = torch.cat(parts)
         return flat

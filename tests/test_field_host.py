@@ -1,0 +1,132 @@
+"""CPU tests of the DEVICE arithmetic: zkdl_b200/csrc/{field,fr_device,g1,g1_device}.cuh compiled for the host
+(tests/host_shim.cpp; the PTX carry-chain primitives have a host emulation) and checked against the oracle / big ints.
+This is the code the kernels instantiate, exercised without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+rng = np.random.default_rng(99)
+
+
+@pytest.fixture(scope="module")
+def hs():
+    out = os.path.join(HERE, "_build", "host_shim.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "host_shim.cpp")
+    deps = [src] + [os.path.join(HERE, "..", "zkdl_b200", "csrc", f) for f in ("field.cuh", "fr_device.cuh", "g1.cuh", "g1_device.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", out, src])
+    return C.CDLL(out)
+
+
+def p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def rand(n, w):
+    P = orc.FR_P if w == 8 else orc.FQ_P
+    vals = [int.from_bytes(rng.bytes(64), "little") % P for _ in range(n)] + [0, 1, P - 1, P - 2, (1 << (32 * w)) % P]
+    return orc.to_limbs(vals, w)
+
+
+def test_field_ops_match_bigints(hs):
+    for w, pre, P in ((8, "fr", orc.FR_P), (12, "fq", orc.FQ_P)):
+        a, b = rand(500, w), rand(500, w)[::-1].copy()
+        ai, bi = orc.from_limbs(a), orc.from_limbs(b)
+        Rinv = pow(1 << (32 * w), -1, P)
+        for op, f in (("mul", lambda x, y: x * y * Rinv % P), ("add", lambda x, y: (x + y) % P), ("sub", lambda x, y: (x - y) % P)):
+            o = np.zeros_like(a)
+            getattr(hs, f"hs_{pre}_{op}")(p(a), p(b), p(o), C.c_size_t(len(a)))
+            assert orc.from_limbs(o) == [f(x, y) for x, y in zip(ai, bi)], (pre, op)
+    a = rand(100, 8); o = np.zeros_like(a)
+    hs.hs_fr_mont(p(a), p(o), C.c_size_t(len(a))); assert np.array_equal(o, orc.fr_mont(a))
+    hs.hs_fr_unmont(p(a), p(o), C.c_size_t(len(a))); assert np.array_equal(o, orc.fr_unmont(a))
+    q = rand(6, 12); q = q[(q != 0).any(axis=1)]; o = np.zeros_like(q)
+    hs.hs_fq_inv(p(q), p(o), C.c_size_t(len(q)))
+    one = orc.to_limbs([orc.FQ_R], 12)[0]
+    assert all((r == one).all() for r in orc.fq_mul(q, o))
+
+
+def test_sumcheck_pair_math(hs):
+    n = 200
+    a0, a1, b0, b1, e, x = (rand(n - 5, 8) for _ in range(6))
+    x = x[:1].copy()
+    o = np.zeros_like(a0)
+    hs.hs_fold_pair(p(a0), p(a1), p(x), p(o), C.c_size_t(n))
+    xs = np.repeat(x, n, 0)
+    assert np.array_equal(o, orc.fr_add(a0, orc.fr_mul(xs, orc.fr_sub(a1, a0))))
+    da, db = orc.fr_sub(a1, a0), orc.fr_sub(b1, b0)
+    c0, c2 = orc.fr_mul(a0, b0), orc.fr_mul(da, db)
+    c1 = orc.fr_add(orc.fr_mul(a0, db), orc.fr_mul(b0, da))
+    for weighted in (0, 1):
+        c = np.zeros((3 * n, 8), np.uint32); ao, bo = np.zeros_like(a0), np.zeros_like(a0)
+        hs.hs_ip_pair(p(a0), p(a1), p(b0), p(b1), p(e), p(x), weighted, p(c), p(ao), p(bo), C.c_size_t(n))
+        wgt = (lambda v: orc.fr_mul(e, v)) if weighted else (lambda v: v)
+        assert np.array_equal(c[0::3], wgt(c0)) and np.array_equal(c[1::3], wgt(c1)) and np.array_equal(c[2::3], wgt(c2))
+        assert np.array_equal(ao, orc.fr_add(a0, orc.fr_mul(xs, da))) and np.array_equal(bo, orc.fr_add(b0, orc.fr_mul(xs, db)))
+    c = np.zeros((3 * n, 8), np.uint32); ao = np.zeros_like(a0)
+    hs.hs_bin_pair(p(a0), p(a1), p(e), p(x), p(c), p(ao), C.c_size_t(n))
+    assert np.array_equal(c[0::3], orc.fr_mul(e, orc.fr_sub(orc.fr_mul(a0, a0), a0)))
+    assert np.array_equal(c[1::3], orc.fr_mul(e, orc.fr_sub(orc.fr_mul(orc.fr_add(a0, a0), da), da)))
+    assert np.array_equal(c[2::3], orc.fr_mul(e, orc.fr_mul(da, da)))
+
+
+def test_quantise_and_relu_device_functions(hs):
+    fs = np.concatenate([rng.standard_normal(500).astype(np.float32) * 3, np.array([0.0, -0.0, 2.5 / 65536, -2.5 / 65536, 1e9, -1e9, np.inf, -np.inf, np.nan], np.float32)])
+    o = np.zeros((len(fs), 8), np.uint32)
+    hs.hs_float_to_fr(p(fs), p(o), C.c_size_t(len(fs)))
+    assert np.array_equal(o, orc.float_to_fr(fs.reshape(-1, 1), len(fs), 1))
+    xs = [int(v) for v in rng.integers(-(1 << 46), 1 << 46, size=400)] + [0, 1, -1, 32767, 32768, -32768, (1 << 47) - 1, -(1 << 47), 1 << 47, -(1 << 47) - 1]
+    X = orc.fr_from_ints(xs)
+    n = len(xs)
+    q, r = np.zeros(n, np.uint32), np.zeros(n, np.uint16); pos, bad = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    hs.hs_relu(p(X), p(q), p(r), p(pos), p(bad), C.c_size_t(n))
+    Z, sign, mag, rem, nbad = orc.relu(X)
+    assert int(bad.sum()) == nbad == 2
+    magb = np.array(orc.fr_to_ints(mag)).reshape(n, 32); remb = np.array(orc.fr_to_ints(rem)).reshape(n, 16)
+    for i in range(n):
+        assert [(int(q[i]) >> k) & 1 for k in range(32)] == list(magb[i]) and [(int(r[i]) >> k) & 1 for k in range(16)] == list(remb[i])
+    assert list(pos) == orc.fr_to_ints(sign)
+
+
+@pytest.mark.parametrize("c", [4, 8, 11, 12, 13, 16])
+def test_signed_digit_recoding(hs, c):
+    W = (255 + c - 1) // c
+    vals = [int.from_bytes(rng.bytes(40), "little") % orc.FR_P for _ in range(200)] + [0, 1, orc.FR_P - 1, (orc.FR_P - 1) // 2, (orc.FR_P + 1) // 2, (1 << 255) - 1 - orc.FR_P]
+    raw = vals + [(1 << 256) - 1, orc.FR_P, orc.FR_P + 5, 2 * orc.FR_P + 1]       # non-canonical raw limbs are reduced mod r
+    for mont, src in ((0, raw), (1, vals)):
+        s = orc.to_limbs(src, 8)
+        d = np.zeros((len(src), W), np.int32); sg = np.zeros(len(src), np.int32)
+        hs.hs_digits(p(s), mont, c, W, p(d), p(sg), C.c_size_t(len(src)))
+        for v, row, neg in zip(src, d, sg):
+            x = (v * pow(orc.FR_R, -1, orc.FR_P)) % orc.FR_P if mont else v % orc.FR_P
+            assert all(-(1 << (c - 1)) < int(t) <= (1 << (c - 1)) for t in row)
+            got = sum(int(t) << (c * w) for w, t in enumerate(row))
+            assert (-got if neg else got) % orc.FR_P == x
+            assert got <= (orc.FR_P - 1) // 2
+
+
+def test_g1_xyzz_formulas_match_oracle(hs):
+    G = orc.g1_generator()
+    ks = orc.to_limbs([int.from_bytes(rng.bytes(31), "little") for _ in range(12)])
+    P = orc.g1_mul(G, ks, fast=True); Q = orc.g1_mul(G, ks[::-1].copy(), fast=True)
+    Q[0] = P[0]; Q[1] = orc.g1_neg(P[1:2])[0]; Q[2, 24:] = 0; P[3, 24:] = 0; P[4, 24:] = 0; Q[4, 24:] = 0
+    n = len(P)
+    o = np.zeros_like(P)
+    hs.hs_g1_add(p(P), p(Q), p(o), C.c_size_t(n)); assert orc.g1_eq(o, orc.g1_add(P, Q)).all()
+    hs.hs_g1_dbl(p(P), p(o), C.c_size_t(n)); assert orc.g1_eq(o, orc.g1_double(P)).all()
+    aff, inf = orc.g1_to_affine(Q)
+    aff2 = np.zeros_like(aff)
+    hs.hs_g1_to_affine(p(Q), p(aff2), C.c_size_t(n)); assert np.array_equal(aff2, aff)       # affine form is canonical
+    for negate in (0, 1):
+        hs.hs_g1_madd(p(P), p(aff), negate, p(o), C.c_size_t(n))
+        exp = orc.g1_add(P, orc.g1_neg(Q) if negate else Q)
+        assert orc.g1_eq(o, exp).all()
+    kk = np.array([0, 1, 2, 3, 7, 8, 255, 1023, 2047, 32767, 5, 6], np.uint32)
+    hs.hs_g1_mul_small(p(P), p(kk), p(o), C.c_size_t(n))
+    assert orc.g1_eq(o, orc.g1_mul(P, orc.to_limbs([int(v) for v in kk]), fast=True)).all()

@@ -14,17 +14,24 @@ def partition_layers(n_layers, world, rank):
     return fc, relu
 
 
-def gather_proof(flat, world, rank, device):
-    """Gathers each rank's flat proof tensor on rank 0.  Returns the list of per-rank tensors on rank 0, None elsewhere."""
+def gather_proof(flat, world, rank, device, sizes=None):
+    """Gathers each rank's flat proof tensor on rank 0.  Returns the list of per-rank tensors on rank 0, None elsewhere.
+    `sizes` (elements per rank) is known in advance for a given model shape: passing it avoids the size exchange and
+    its host synchronisation."""
     if world == 1:
         return [flat]
-    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([flat.numel()], dtype=torch.int64, device=device))
-    mx = int(max(int(s.item()) for s in sizes))
-    buf = torch.zeros(mx, dtype=flat.dtype, device=device)
-    buf[: flat.numel()] = flat
+    if sizes is None:
+        szs = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(szs, torch.tensor([flat.numel()], dtype=torch.int64, device=device))
+        sizes = [int(s.item()) for s in szs]
+    mx = max(sizes)
+    if flat.numel() == mx:
+        buf = flat
+    else:
+        buf = torch.zeros(mx, dtype=flat.dtype, device=device)
+        buf[: flat.numel()] = flat
     outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
     dist.gather(buf, outs, dst=0)
     if rank != 0:
         return None
-    return [o[: int(s.item())] for o, s in zip(outs, sizes)]
+    return [o[:s] for o, s in zip(outs, sizes)]
