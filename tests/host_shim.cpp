@@ -16,6 +16,14 @@ void hs_fq_mul(const Fq* a, const Fq* b, Fq* o, size_t n) { for (size_t i = 0; i
 void hs_fq_add(const Fq* a, const Fq* b, Fq* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = add(a[i], b[i]); }
 void hs_fq_sub(const Fq* a, const Fq* b, Fq* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = sub(a[i], b[i]); }
 void hs_fq_inv(const Fq* a, Fq* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = fq_inv(a[i]); }
+// lazy reduction: out[i] = sum_{t<k} a[i*k+t] * b[i*k+t] / R mod p through the unreduced wide accumulator
+void hs_fr_dot_lazy(const Fr* a, const Fr* b, Fr* o, size_t n, size_t k) {
+  for (size_t i = 0; i < n; ++i) {
+    WideAcc<FrParams> w; wide_zero(w);
+    for (size_t t = 0; t < k; ++t) wide_mac(w, a[i * k + t], b[i * k + t]);
+    o[i] = wide_reduce(w);
+  }
+}
 // per-pair sumcheck math
 void hs_fold_pair(const Fr* a0, const Fr* a1, const Fr* x, Fr* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = fold_pair(a0[i], a1[i], *x); }
 void hs_ip_pair(const Fr* a0, const Fr* a1, const Fr* b0, const Fr* b1, const Fr* e, const Fr* x, int weighted, Fr* c, Fr* ao, Fr* bo, size_t n) {

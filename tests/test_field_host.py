@@ -52,6 +52,20 @@ def test_field_ops_match_bigints(hs):
     assert all((r == one).all() for r in orc.fq_mul(q, o))
 
 
+@pytest.mark.parametrize("k", [1, 2, 8, 16])
+def test_lazy_dot_product(hs, k):
+    n = 60
+    a, b = rand(n * k - 5, 8), rand(n * k - 5, 8)[::-1].copy()
+    if k >= 8:                                   # worst case: every operand p - 1
+        a[: 2 * k] = orc.to_limbs([orc.FR_P - 1] * (2 * k)); b[: 2 * k] = orc.to_limbs([orc.FR_P - 1] * (2 * k))
+    o = np.zeros((n, 8), np.uint32)
+    hs.hs_fr_dot_lazy(p(a), p(b), p(o), C.c_size_t(n), C.c_size_t(k))
+    ai, bi = orc.from_limbs(a), orc.from_limbs(b)
+    Rinv = pow(1 << 256, -1, orc.FR_P)
+    exp = [sum(ai[i * k + t] * bi[i * k + t] for t in range(k)) * Rinv % orc.FR_P for i in range(n)]
+    assert orc.from_limbs(o) == exp
+
+
 def test_sumcheck_pair_math(hs):
     n = 200
     a0, a1, b0, b1, e, x = (rand(n - 5, 8) for _ in range(6))

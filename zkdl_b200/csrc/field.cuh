@@ -257,6 +257,68 @@ ZK_HD bool gte(const Fe<PR>& a, const Fe<PR>& b) {                          // S
   return subc(0u, 0u) == 0u;
 }
 
+// ---- lazy reduction: sums of products accumulated unreduced, one Montgomery reduction at the end.
+// NOTE (measured, profiles/README.md): a fold kernel built on this (8 products + 1 reduction instead of 7 Montgomery
+// products) ran 22 % SLOWER on B200 than k_fr_fold_multi<3>: propagating carries to the top of the 18-limb accumulator
+// moves ~110 IADD3 per product onto the ALU pipe and lengthens the dependent chains.  Kept (host-tested) for the matmul /
+// dot-product shapes where k is large; not used on the proving path.
+// A dot product sum_t a_t * b_t of k Montgomery values costs k * N^2 wide multiplies + one reduction instead of
+// k * (2 N^2 + N).  The accumulator is the exact integer sum (2N+2 limbs, carries propagated to the top), so the result
+// is the same canonical field element as the sum of the k Montgomery products.
+template <class PR>
+struct WideAcc {
+  static constexpr int N = PR::N, L = 2 * PR::N + 2;
+  uint32_t ev[L], od[L];                       // value = EV + 2^32 * OD
+};
+template <class PR>
+ZK_HD void wide_zero(WideAcc<PR>& w) { _Pragma("unroll") for (int i = 0; i < WideAcc<PR>::L; ++i) { w.ev[i] = 0; w.od[i] = 0; } }
+// acc[0..N) += x[xoff], x[xoff+2], ... (N/2 limbs) * w as aligned pairs, carry propagated through acc[N..top)
+template <int N>
+ZK_HD void wide_chain(uint32_t* acc, const uint32_t* x, uint32_t w, const int TOP) {   // TOP: limbs from acc to the top (constant after unrolling)
+  acc[0] = mad_lo_cc(x[0], w, acc[0]);
+  acc[1] = madc_hi_cc(x[0], w, acc[1]);
+  _Pragma("unroll") for (int j = 2; j < N; j += 2) {
+    acc[j] = madc_lo_cc(x[j], w, acc[j]);
+    acc[j + 1] = madc_hi_cc(x[j], w, acc[j + 1]);
+  }
+  _Pragma("unroll") for (int j = N; j < 2 * N + 2; ++j) {
+    if (j < TOP - 1) acc[j] = addc_cc(acc[j], 0u);
+    else if (j == TOP - 1) acc[j] = addc(acc[j], 0u);
+  }
+}
+template <class PR>
+ZK_HD void wide_mac(WideAcc<PR>& w, const Fe<PR>& a, const Fe<PR>& b) {          // w += a * b (integers)
+  constexpr int N = PR::N, L = WideAcc<PR>::L;
+  _Pragma("unroll") for (int i = 0; i < N; i += 2) {
+    // b limb i (even): even limbs of a land on even positions i+j -> ev[i+j]; odd limbs on odd positions -> od[i+j-1]
+    wide_chain<N>(w.ev + i, a.v, b.v[i], L - i);
+    wide_chain<N>(w.od + i, a.v + 1, b.v[i], L - i);
+    // b limb i+1 (odd): even limbs of a land on odd positions i+1+j -> od[i+j]; odd limbs on even positions -> ev[i+1+j]
+    wide_chain<N>(w.od + i, a.v, b.v[i + 1], L - i);
+    wide_chain<N>(w.ev + i + 2, a.v + 1, b.v[i + 1], L - i - 2);
+  }
+}
+// Montgomery-reduce the accumulated integer T: T / R mod p, canonical.  Valid for Fr (R < 5p) and up to 2^32 products.
+template <class PR>
+ZK_HD Fe<PR> wide_reduce(const WideAcc<PR>& w) {
+  constexpr int N = PR::N, L = WideAcc<PR>::L;
+  uint32_t t[L];
+  t[0] = w.ev[0];
+  t[1] = add_cc(w.ev[1], w.od[0]);
+  _Pragma("unroll") for (int i = 2; i < L - 1; ++i) t[i] = addc_cc(w.ev[i], w.od[i - 1]);
+  t[L - 1] = addc(w.ev[L - 1], w.od[L - 2]);
+  Fe<PR> lo, hi, one = Fe<PR>::zero();
+  one.v[0] = 1;
+  _Pragma("unroll") for (int i = 0; i < N; ++i) { lo.v[i] = t[i]; hi.v[i] = t[N + i]; }
+  // T = t[2N] * R^2 + hi * R + lo, so T / R = t[2N] * R + hi + lo / R  (mod p).  R mod p is the Montgomery ONE; t[2N] is
+  // at most (number of products) / 4 (p^2 < R^2 / 4), t[2N+1] is zero for any sum of fewer than 2^32 products.
+  _Pragma("unroll") for (int i = 0; i < 5; ++i) final_sub(hi);          // hi < R < 5p (Fr: R = 4.4p; Fq callers: R = 9.9p, not used)
+  Fe<PR> r = add(hi, mul_impl(lo, one));                               // lo / R mod p
+  const Fe<PR> rmodp = Fe<PR>::one();
+  for (uint32_t c = 0; c < t[2 * N]; ++c) r = add(r, rmodp);
+  return r;
+}
+
 typedef Fe<FrParams> Fr;
 typedef Fe<FqParams> Fq;
 
