@@ -263,6 +263,25 @@ int main(int argc, char** argv) {
         cudaDeviceSynchronize(); double t1 = now();
         if (r) printf("{\"what\":\"ref_open\",\"log_dim\":%u,\"seconds\":%.6f}\n", k, t1 - t0);
       }
+    } else if (what == "layer") {    // one hidden layer of the demo MLP: zkReLU::prove + zkFC::prove, 2^k x 2^k weights, batch B
+      uint k = atoi(argv[3]); uint B = argc > 5 ? atoi(argv[5]) : 256; uint I = 1u << k, O = 1u << k;
+      uint ng = 1u << ((ceilLog2(I * O) + 1) / 2);
+      Commitment G(ng, G1Jacobian_generator);
+      { auto ks = seeded_vec(ng, 7); FrTensor kt(ng, ks.data()); G *= kt; }
+      FrTensor Wt = rand_small(I * O, 13, 1);
+      zkFC fc(I, O, Wt, G);                                            // commits the weights (untimed, as in demo.cu)
+      FrTensor X = rand_small(B * I, 16, 2);
+      FrTensor Z = fc(X);
+      zkReLU relu; FrTensor A = relu(Z);
+      for (int r = 0; r < reps + 1; ++r) {
+        cudaDeviceSynchronize(); double t0 = now();
+        relu.prove(Z, A);
+        cudaDeviceSynchronize(); double t1 = now();
+        fc.prove(X, Z, G);
+        cudaDeviceSynchronize(); double t2 = now();
+        if (r) printf("{\"what\":\"layer_prove\",\"log_dim\":%u,\"batch\":%u,\"relu_seconds\":%.6f,\"fc_seconds\":%.6f,\"seconds\":%.6f}\n", k, B, t1 - t0, t2 - t1, t2 - t0);
+        fflush(stdout);
+      }
     } else if (what == "relu") {     // zkReLU::prove at n = 2^k
       uint k = atoi(argv[3]); uint n = 1u << k;
       FrTensor Z = rand_small(n, 30, 3);
@@ -277,6 +296,6 @@ int main(int argc, char** argv) {
     printf("{\"cuda_status\":%d}\n", (int)cudaGetLastError());
     return 0;
   }
-  fprintf(stderr, "usage: ref_harness run <in> <out> | time <fold|fc|msm|open|relu> <log_n> [reps] [batch]\n");
+  fprintf(stderr, "usage: ref_harness run <in> <out> | time <fold|fc|msm|open|relu|layer> <log_n> [reps] [batch]\n");
   return 1;
 }
