@@ -70,6 +70,25 @@ int scratch_free(void* p, cudaStream_t s) {
   }
   return ZK_OK;
 }
+SideStream& side_stream(int idx) {
+  static thread_local SideStream pool[4];
+  return pool[idx & 3];
+}
+int SideStream::fork(cudaStream_t main) {
+  if (!stream) {
+    ZK_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ZK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  ZK_CUDA(cudaEventRecord(ev_fork, main));
+  ZK_CUDA(cudaStreamWaitEvent(stream, ev_fork, 0));
+  return ZK_OK;
+}
+int SideStream::join(cudaStream_t main) {
+  ZK_CUDA(cudaEventRecord(ev_join, stream));
+  ZK_CUDA(cudaStreamWaitEvent(main, ev_join, 0));
+  return ZK_OK;
+}
 int num_sms() {
   static int n = 0;
   if (!n) {

@@ -38,6 +38,15 @@ struct Scratch {                       // RAII helper used inside the C-ABI func
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Fork/join of independent sub-proofs onto side streams (per host thread): fork() makes side stream `idx` wait for the
+// work enqueued so far on `main`; join() makes `main` wait for everything enqueued on the side stream since.
+struct SideStream {
+  cudaStream_t stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int fork(cudaStream_t main);
+  int join(cudaStream_t main);
+};
+SideStream& side_stream(int idx);          // idx < 4
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int num_sms();
 

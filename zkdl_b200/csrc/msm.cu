@@ -518,15 +518,10 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   if (khi > 0) ZK_REQUIRE(!(ncom <= ((size_t)1 << (khi - 1)) || ncom > ((size_t)1 << khi)), ZK_ERR_DIM, "Incompatible dimensions");
   // com(u_hi) and the opening proper are independent: fork the commitment-vector evaluation onto a side stream so its
   // latency-bound bucket reduction overlaps the opening MSM (joined before returning).
-  static thread_local cudaStream_t side = nullptr; static thread_local cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // per host thread
-  if (!side) {
-    ZK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    ZK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  }
+  SideStream& ss = side_stream(0);
   Scratch uq, E, tf; int rc;
-  ZK_CUDA(cudaEventRecord(ev_fork, st));
-  ZK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  if ((rc = ss.fork(st))) return rc;
+  cudaStream_t side = ss.stream;
   {
     Scratch uqs, Es;
     if ((rc = uqs.alloc(sizeof(Fr) * (khi ? khi : 1), side))) return rc;
@@ -535,7 +530,6 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
     if ((rc = build_eq_table(uqs.as<Fr>(), u_hi, (int)khi, 0, Es.as<Fr>(), side))) return rc;
     if ((rc = msm_run(com_table, Es.as<Fr>(), 1, 1, 0, com_eval, side))) return rc;
   }
-  ZK_CUDA(cudaEventRecord(ev_join, side));
   // t.partial_me(u_hi, |gens|)
   size_t w = gens->n;
   if (khi > 0) ZK_REQUIRE(nt > w * ((size_t)1 << (khi - 1)), ZK_ERR_DIM, "Incompatible dimensions");   // fr-tensor.cu:372
@@ -544,8 +538,8 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   if ((rc = tf.alloc(sizeof(Fr) * tf_n, st))) return rc;
   if ((rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st))) return rc;
   rc = me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
-  ZK_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-  return rc;
+  int rj = ss.join(st);
+  return rc ? rc : rj;
 }
 
 }  // namespace zk

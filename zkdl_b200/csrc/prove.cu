@@ -31,21 +31,25 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
   size_t kb = ilog2(B), ki = ilog2(I), ko = ilog2(O);
   ZK_REQUIRE(((size_t)1 << kb) == B && ((size_t)1 << ki) == I && ((size_t)1 << ko) == O, ZK_ERR_DIM, "Incompatible dimensions 1");
   int rc;
-  Scratch Xr, Wr;
-  if ((rc = Xr.alloc(sizeof(Fr) * I, st))) return rc;
-  if ((rc = Wr.alloc(sizeof(Fr) * I, st))) return rc;
-  // X.partial_me(u_bs, inputSize), weights.partial_me(u_out_dim, 1)   (zkfc.cu:139)
-  if ((rc = zkdl_fr_partial_me(X, B * I, u_bs_host, kb, I, Xr.as<zkdl_fr_t>(), stream))) return rc;
-  if ((rc = zkdl_fr_partial_me(W, I * O, u_out_host, ko, 1, Wr.as<zkdl_fr_t>(), stream))) return rc;
-  if ((rc = zkdl_ip_sumcheck(Xr.as<zkdl_fr_t>(), Wr.as<zkdl_fr_t>(), I, u_in_host, ki, proof_fr, stream))) return rc;
-  // Z(u_out || u_bs)   (zkfc.cu:141-143)
+  // The matmul sumcheck and the commitment opening are independent: the sumcheck part runs on a side stream.
+  SideStream& ss = side_stream(1);
+  if ((rc = ss.fork(st))) return rc;
+  void* sst = reinterpret_cast<void*>(ss.stream);
   size_t nip = 3 * ki + 2;
   {
+    Scratch Xr, Wr;
+    if ((rc = Xr.alloc(sizeof(Fr) * I, ss.stream))) return rc;
+    if ((rc = Wr.alloc(sizeof(Fr) * I, ss.stream))) return rc;
+    // X.partial_me(u_bs, inputSize), weights.partial_me(u_out_dim, 1)   (zkfc.cu:139)
+    if ((rc = zkdl_fr_partial_me(X, B * I, u_bs_host, kb, I, Xr.as<zkdl_fr_t>(), sst))) return rc;
+    if ((rc = zkdl_fr_partial_me(W, I * O, u_out_host, ko, 1, Wr.as<zkdl_fr_t>(), sst))) return rc;
+    if ((rc = zkdl_ip_sumcheck(Xr.as<zkdl_fr_t>(), Wr.as<zkdl_fr_t>(), I, u_in_host, ki, proof_fr, sst))) return rc;
+    // Z(u_out || u_bs)   (zkfc.cu:141-143)
     zkdl_fr_t uz[64];
     ZK_REQUIRE(ko + kb <= 64, ZK_ERR_DIM, "Incompatible dimensions");
     for (size_t i = 0; i < ko; ++i) uz[i] = u_out_host[i];
     for (size_t i = 0; i < kb; ++i) uz[ko + i] = u_bs_host[i];
-    if ((rc = zkdl_fr_me(Z, B * O, uz, ko + kb, proof_fr + nip, stream))) return rc;
+    if ((rc = zkdl_fr_me(Z, B * O, uz, ko + kb, proof_fr + nip, sst))) return rc;
   }
   // generators.open(weights, com, u_out || u_in)   (zkfc.cu:144)
   {
@@ -57,7 +61,7 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
                   reinterpret_cast<G1Jac*>(proof_g1 + 1), reinterpret_cast<Fr*>(proof_fr + nip + 1), st);
     if (rc) return rc;
   }
-  return ZK_OK;
+  return ss.join(st);
 }
 
 size_t zkdl_zkrelu_proof_size(size_t n) {
