@@ -69,7 +69,7 @@ class MLPProver:
                 cur = a
         return self.Z[-1]
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=True):
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
         fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); challenges are drawn for
         every layer regardless, so a layer's proof does not depend on which rank produced it.
@@ -78,7 +78,10 @@ class MLPProver:
         the bandwidth-bound sumcheck passes of another.  With threads=True each stream is fed by its own host thread
         (ctypes releases the GIL, the library is thread-safe), so the ~1200 kernel launches of a proof are issued in
         parallel instead of from one core."""
+        import os
         import torch
+        if threads is None:                              # ZKDL_PROVE_THREADS=0: issue from the calling thread (NVTX-scoped profiling)
+            threads = os.environ.get("ZKDL_PROVE_THREADS", "1") != "0"
         ctr = [seed]
 
         def rv(k):
