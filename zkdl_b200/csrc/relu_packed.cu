@@ -89,7 +89,7 @@ extern __shared__ __align__(16) unsigned char pk_smem[];
 // One pass over the packed words: rounds 0, 1, 2 of the binary sumcheck + the folded table a^(3).
 // partials[blockIdx][7] = {S0, S1[3], S2[3]}
 template <int Q, class T>
-__global__ void __launch_bounds__(256) k_bin_packed3(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e_hi, const Fr* __restrict__ lut,
+__global__ void __launch_bounds__(512) k_bin_packed3(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e_hi, const Fr* __restrict__ lut,
                                                      Fr* __restrict__ a3, Fr* __restrict__ partials) {
   using PL = PackLayout<Q>;
   Fr* sm = reinterpret_cast<Fr*>(pk_smem);
@@ -219,16 +219,12 @@ static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkd
   if ((rc = ehi.alloc(sizeof(Fr) * n, st))) return rc;
   if ((rc = build_eq_table(ud.as<Fr>() + PL::LOGQ, u_host + PL::LOGQ, (int)L, 0, ehi.as<Fr>(), st))) return rc;
   if ((rc = a3.alloc(sizeof(Fr) * n * PL::N2, st))) return rc;
-  unsigned grid = (unsigned)num_sms();
-  if ((size_t)grid * 256 > n) grid = div_up(n, 256);
+  unsigned grid = (unsigned)num_sms();                     // one CTA per SM (the look-up tables take 64-119 KB of shared memory)
+  if ((size_t)grid * 512 > n) grid = div_up(n, 512);
   if ((rc = parts.alloc(sizeof(Fr) * 7 * grid, st))) return rc;
-  static bool attr_set = false;
   size_t smem = sizeof(Fr) * PL::TOTAL;
-  if (!attr_set || true) {
-    ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 256, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), a3.as<Fr>(), parts.as<Fr>()));
+  ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), a3.as<Fr>(), parts.as<Fr>()));
   ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, proof_sc));
   // rounds 3.. on the folded table: binary_sumcheck(a3, u[3:], v[3:]) has exactly the remaining rounds and the final a(0)
   if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n * PL::N2, u_host + 3, v_host + 3, k - 3, reinterpret_cast<zkdl_fr_t*>(proof_sc + 9), st))) return rc;
