@@ -35,3 +35,22 @@ def gather_proof(flat, world, rank, device, sizes=None):
     if rank != 0:
         return None
     return [o[:s] for o, s in zip(outs, sizes)]
+
+
+def shard_range(n, world, rank):
+    """Contiguous point range [lo, hi) of rank `rank` for an MSM over n (base, scalar) pairs."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def msm_sharded(msm_local, g1_sum, part_like, world):
+    """Single large MSM partitioned by point range: every rank computes the MSM of its own (bases, scalars) slice
+    (`msm_local()` -> one Jacobian point, [1, 36] limbs), the P partial points (144 B each) are all-gathered and every
+    rank adds them locally with `g1_sum` (G1 addition is not an NCCL reduction op).  Returns the full MSM on every rank."""
+    part = msm_local()
+    if world == 1:
+        return part
+    parts = [torch.empty_like(part_like if part_like is not None else part) for _ in range(world)]
+    dist.all_gather(parts, part)
+    return g1_sum(torch.cat(parts))
