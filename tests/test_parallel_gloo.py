@@ -73,3 +73,84 @@ def test_shard_ranges_and_sharded_msm_world2_gloo():
     for p in procs:
         p.join(120); assert p.exitcode == 0
     assert all(it[3] == 45 for it in items)          # every rank ends with the full sum
+
+
+class OracleOps:
+    """Same interface as parallel.CapiOps with the CPU oracle as the local primitive (tests only)."""
+
+    def local(self, kind, tables, u, v):
+        import numpy as np
+        from oracle import oracle as orc
+        t = [np.asarray(x, dtype=np.uint32) for x in tables]
+        if kind == "bin":
+            return orc.bin_sumcheck(t[0], u, v)
+        if kind == "hp":
+            return orc.hp_sumcheck(t[0], t[1], u, v)
+        return orc.ip_sumcheck(t[0], t[1], u)
+
+    def eq_weights(self, u_hi, world):
+        import numpy as np
+        from oracle import oracle as orc
+        one = orc.fr_mont(orc.to_limbs([1]))[0]
+        out = []
+        for r in range(world):
+            e = np.zeros((world, 8), np.uint32); e[r] = one
+            out.append(orc.fr_me(e, u_hi))
+        return out
+
+    def weighted_sum(self, parts, weights):
+        from oracle import oracle as orc
+        acc = None
+        for p, w in zip(parts, weights):
+            t = p if w is None else orc.fr_bcast(p, w, "mul")
+            acc = t if acc is None else orc.fr_add(acc, t)
+        return acc
+
+    def stack(self, rows):
+        import numpy as np
+        return np.stack(list(rows))
+
+    def cat(self, parts):
+        import numpy as np
+        return np.concatenate(list(parts))
+
+
+def _sc_worker(rank, world, port, q):
+    import numpy as np
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    k = 6; n = 1 << k
+    def rnd(m):
+        x = rng.integers(0, 1 << 32, size=(m, 8), dtype=np.uint64).astype(np.uint32); x[:, 7] %= 1944954707; return x
+    a, b, u, v = rnd(n), rnd(n), rnd(k), rnd(k)
+    lo, hi = parallel.shard_range(n, world, rank)
+
+    def all_gather(x):
+        t = torch.from_numpy(np.ascontiguousarray(x).view(np.int32))
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [o.numpy().view(np.uint32) for o in outs]
+
+    ops = OracleOps()
+    res = {}
+    for kind, tabs in (("bin", [a[lo:hi]]), ("hp", [a[lo:hi], b[lo:hi]]), ("ip", [a[lo:hi], b[lo:hi]])):
+        got = parallel.sumcheck_sharded(kind, ops, tabs, u, v, world, rank, all_gather)
+        full = {"bin": lambda: orc.bin_sumcheck(a, u, v), "hp": lambda: orc.hp_sumcheck(a, b, u, v), "ip": lambda: orc.ip_sumcheck(a, b, u)}[kind]()
+        res[kind] = bool(np.array_equal(got, full))
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_sharded_sumcheck_world2_gloo_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 1000
+    procs = [ctx.Process(target=_sc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    items = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(120); assert p.exitcode == 0
+    for rank, res in items:
+        assert res == {"bin": True, "hp": True, "ip": True}, (rank, res)

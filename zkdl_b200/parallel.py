@@ -54,3 +54,72 @@ def msm_sharded(msm_local, g1_sum, part_like, world):
     parts = [torch.empty_like(part_like if part_like is not None else part) for _ in range(world)]
     dist.all_gather(parts, part)
     return g1_sum(torch.cat(parts))
+
+
+# ------------------------------------------------------------------------------------------------ sharded sumcheck
+# A 2^k table split by its LEADING log2(P) variables: rank r holds the contiguous slice [r * 2^kl, (r+1) * 2^kl),
+# kl = k - log2 P.  The folds bind the least-significant variable first (fr-tensor.cu:404-406), so the first kl rounds
+# are purely local.  Round j < kl of the global sumcheck is
+#     S_j = sum_r eq(u[kl:], r) * S_j^(r)      (binary / Hadamard: the eq weight factorises over the rank bits)
+#     S_j = sum_r S_j^(r)                      (inner product: no weights)
+# where S_j^(r) is what the single-GPU routine emits on rank r's slice with challenges u[:kl], v[:kl]; the remaining
+# log2 P rounds run on the P-vector of the slices' final values.  Communication: ONE all-gather of 3*kl + 1 (or 2) field
+# elements per rank (all challenges are known up front), then a few dozen local modular operations.
+class CapiOps:
+    """The sharded-sumcheck arithmetic through libzkdl_b200 (GPU)."""
+
+    def __init__(self):
+        from . import capi
+        self.zk = capi
+
+    def local(self, kind, tables, u, v):
+        zk = self.zk
+        if kind == "bin":
+            return zk.bin_sumcheck(tables[0], u, v)
+        if kind == "hp":
+            return zk.hp_sumcheck(tables[0], tables[1], u, v)
+        return zk.ip_sumcheck(tables[0], tables[1], u)
+
+    def eq_weights(self, u_hi, world):
+        """eq(u_hi, r) for r < world: the multilinear extension of the r-th unit vector evaluated at u_hi."""
+        import numpy as np
+        zk = self.zk
+        one = np.array([4294967294, 1, 215042, 1485092858, 3971764213, 2576109551, 2898593135, 405057881], dtype=np.uint32)
+        out = []
+        for r in range(world):
+            e = np.zeros((world, 8), np.uint32); e[r] = one
+            out.append(zk.to_host(zk.fr_me(zk.to_device(e), u_hi))[0])
+        return out
+
+    def weighted_sum(self, parts, weights):
+        zk = self.zk
+        acc = None
+        for p, w in zip(parts, weights):
+            t = p if w is None else zk.fr_broadcast(zk.OP_MUL, p, w)
+            acc = t if acc is None else zk.fr_elementwise(zk.OP_ADD, acc, t)
+        return acc
+
+    def stack(self, rows):
+        return torch.stack(list(rows))
+
+    def cat(self, parts):
+        return torch.cat(list(parts))
+
+
+def sumcheck_sharded(kind, ops, tables_local, u, v, world, rank, all_gather):
+    """kind in {"bin", "hp", "ip"}; tables_local: this rank's slice(s); u, v: the FULL challenge vectors (host arrays,
+    v ignored for "ip"); all_gather(x) -> list of every rank's x.  Returns the proof, identical to the single-GPU one."""
+    k = len(u)
+    lp = (world - 1).bit_length()
+    assert (1 << lp) == world and k >= lp, "world must be a power of two no larger than the table"
+    kl = k - lp
+    nfin = 1 if kind == "bin" else 2
+    local = ops.local(kind, tables_local, u[:kl], None if kind == "ip" else v[:kl])     # [3*kl + nfin]
+    if world == 1:
+        return local
+    parts = all_gather(local)
+    weights = [None] * world if kind == "ip" else ops.eq_weights(u[kl:], world)
+    rounds = ops.weighted_sum([p[: 3 * kl] for p in parts], weights)
+    finals = [ops.stack([p[3 * kl + i] for p in parts]) for i in range(nfin)]             # P-vectors of a (and b)
+    tail = ops.local(kind, finals, u[kl:], None if kind == "ip" else v[kl:])
+    return ops.cat([rounds, tail])
