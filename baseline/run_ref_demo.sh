@@ -1,31 +1,30 @@
 #!/bin/bash
-# Baseline A smoke run: the UNMODIFIED reference demo (vendored under baseline/_ref, prebuilt with
-# nvcc -arch=sm_100 -std=c++17 -dc -dlto) on the reference's own workload, batch 256 and batch 1.
+# Baseline A smoke run: the UNMODIFIED reference demo (oracle/_ref/demo, built from /root/reference by oracle/build_ref.sh
+# with nvcc -arch=sm_100 -std=c++17 -dc -dlto) on the reference's own workload, batch 256 and batch 1.
 # Usage (from repo root):  gpurun --timeout 900 -- bash baseline/run_ref_demo.sh
+# (bench.py --impl reference is the maintained way to time the reference; this script is kept for manual runs.)
 OUT=$PWD/gpurun_out/ref_demo; mkdir -p "$OUT"
-cd baseline/_ref || exit 1
+DEMO=$PWD/oracle/_ref/demo
+WORK=$(mktemp -d); cd "$WORK" || exit 1
 nvidia-smi > "$OUT/nvidia-smi.txt" 2>&1
-nproc > "$OUT/nproc.txt"; lscpu | grep -E "Model name|^CPU\(s\)" >> "$OUT/nproc.txt"
-# seeded fixture (model.py itself is unseeded): same script, RNG fixed first
 python - > "$OUT/model_py.log" 2>&1 <<'PY'
-import torch
+import torch, torch.nn as nn
 torch.manual_seed(0)
-exec(open('model.py').read())
-m = torch.jit.load('sample_input.pt')
-x = dict(m.named_parameters())['0'].detach()
-save_tensor(x[:1].contiguous(), 'sample_input_b1.pt')
-print('B1 input', x[:1].shape)
+def save_tensor(t, fn):
+    m = nn.Module(); m.register_parameter("0", nn.Parameter(t)); torch.jit.script(m).save(fn)
+d = [784, 1000, 1773, 1773, 1773, 1773, 1773, 1124, 1000]
+layers = []
+for i in range(8):
+    layers.append(nn.Linear(d[i], d[i + 1], bias=False))
+    if i < 7: layers.append(nn.ReLU())
+model = nn.Sequential(*layers).to("cuda").eval()
+x = torch.randn(256, 784).to("cuda")
+save_tensor(x, "sample_input.pt"); save_tensor(x[:1].contiguous(), "sample_input_b1.pt")
+torch.jit.trace(model, x[:1]).save("traced_model.pt")
 PY
-tail -3 "$OUT/model_py.log"
-for i in 1 2 3; do
-  /usr/bin/env bash -c "time ./demo traced_model.pt sample_input.pt" > "$OUT/demo_b256_run$i.log" 2>&1
-  sha256sum demo.out >> "$OUT/demo_b256_run$i.log"; wc -l demo.out >> "$OUT/demo_b256_run$i.log"
-  cat "$OUT/demo_b256_run$i.log"
+for inp in sample_input.pt sample_input_b1.pt; do
+  for i in 1 2; do
+    /usr/bin/env bash -c "time $DEMO traced_model.pt $inp" > "$OUT/demo_${inp%.pt}_run$i.log" 2>&1
+    sha256sum demo.out >> "$OUT/demo_${inp%.pt}_run$i.log"; cat "$OUT/demo_${inp%.pt}_run$i.log"
+  done
 done
-head -c 700 demo.out > "$OUT/demo_b256_out_head.txt"
-for i in 1 2 3; do
-  /usr/bin/env bash -c "time ./demo traced_model.pt sample_input_b1.pt" > "$OUT/demo_b1_run$i.log" 2>&1
-  sha256sum demo.out >> "$OUT/demo_b1_run$i.log"; wc -l demo.out >> "$OUT/demo_b1_run$i.log"
-  cat "$OUT/demo_b1_run$i.log"
-done
-nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,memory.total --format=csv >> "$OUT/nvidia-smi.txt" 2>&1
