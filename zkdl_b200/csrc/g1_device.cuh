@@ -17,7 +17,7 @@ ZK_HD void scalar_prepare(const Fr& s_in, bool mont, Fr& mag, bool& negative) {
   if (!s.is_zero() && !gte(t, s)) { mag = t; negative = true; } else { mag = s; negative = false; }
 }
 
-// bits [pos, pos + c) of a 256-bit little-endian integer, c <= 16
+// bits [pos, pos + c) of a 256-bit little-endian integer, c <= 24
 ZK_HD uint32_t get_bits(const Fr& a, int pos, int c) {
   if (pos >= 256) return 0;
   int limb = pos >> 5, off = pos & 31;

@@ -192,6 +192,18 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
   }
 }
 
+// largest bit length of the normalised scalars |s| (plain-mode window planning)
+__global__ void __launch_bounds__(256) k_msm_max_bits(const Fr* __restrict__ scalars, size_t total, int mont, uint32_t* __restrict__ out) {
+  uint32_t best = 0;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    Fr mag; bool negative;
+    scalar_prepare(scalars[idx], mont != 0, mag, negative);
+    for (int l = 7; l >= 0; --l) if (mag.v[l]) { uint32_t b = l * 32 + 32 - __clz(mag.v[l]); if (b > best) best = b; break; }
+  }
+  for (int o = 16; o > 0; o >>= 1) { uint32_t y = __shfl_down_sync(0xffffffffu, best, o); if (y > best) best = y; }
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(out, best);
+}
+
 // exclusive scan, three phases, tiles of 1024 * 4
 static constexpr int SCAN_T = 1024, SCAN_PER = 4, SCAN_TILE = SCAN_T * SCAN_PER;
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
@@ -435,9 +447,33 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   MsmCfg cfg;
   cfg.n = t->n; cfg.m = m; cfg.full = t->full; cfg.mont = mont;
   cfg.c = c_override ? c_override : pick_c(t, m);
+  int maxbits = 254;
+  if (!cfg.full && !c_override) {
+    // Plain Pippenger (setup-time commitments and the MSM sweep; never on the proving path): one 4-byte read-back of the
+    // largest scalar magnitude lets the windows be planned so that the TOP window is as wide as possible.  A narrow top
+    // window (e.g. 3 bits of a 16-bit scalar under c = 13) funnels all points into a handful of buckets.
+    Scratch mb; int rc0;
+    if ((rc0 = mb.alloc(sizeof(uint32_t), st))) return rc0;
+    ZK_CUDA(cudaMemsetAsync(mb.p, 0, sizeof(uint32_t), st));
+    ZK_LAUNCH(k_msm_max_bits<<<g1_grid(m * cfg.n, 256), 256, 0, st>>>(scalars, m * cfg.n, mont, mb.as<uint32_t>()));
+    uint32_t h = 0;
+    ZK_CUDA(cudaMemcpyAsync(&h, mb.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    maxbits = h ? (int)h : 1;
+    int c0 = cfg.c, best_c = c0, best_top = -1;
+    for (int c = (c0 > 6 ? c0 - 2 : 4); c <= (c0 + 2 < 16 ? c0 + 2 : 16); ++c) {
+      int W = (maxbits + 1 + c - 1) / c;                     // one spare bit for the signed-digit carry
+      int top = maxbits + 1 - (W - 1) * c;                   // bits that reach the top window
+      if (W == 1) top = c;                                   // a single window has no skewed top
+      if (top > 4) top = 4;                                  // 4+ bits in the top window is balanced enough: then stay close to c0
+      if (top > best_top || (top == best_top && abs(c - c0) < abs(best_c - c0))) { best_top = top; best_c = c; }
+    }
+    cfg.c = best_c;
+    if (maxbits + 1 <= 20 && ((size_t)1 << (maxbits + 1)) <= 8 * cfg.n) cfg.c = maxbits + 1 < 4 ? 4 : maxbits + 1;   // one window covers the scalar
+  }
   if (cfg.full) { cfg.c = (cfg.c / TABLE_C) * TABLE_C; if (cfg.c < TABLE_C) cfg.c = TABLE_C; if (cfg.c > 16) cfg.c = 16; }
   cfg.tstep = cfg.c / TABLE_C;
-  cfg.W = (255 + cfg.c - 1) / cfg.c;
+  cfg.W = cfg.full ? (255 + cfg.c - 1) / cfg.c : (maxbits + 1 + cfg.c - 1) / cfg.c;
   cfg.K = 1 << (cfg.c - 1);
   cfg.NG = cfg.full ? 1 : cfg.W;
   size_t nkeys = m * (size_t)cfg.NG * cfg.K;
