@@ -110,6 +110,8 @@ class MLPProver:
             relu(i)
             fc(i)
 
+        self.last_tasks = tasks                       # (kind, layer, challenges): what a verifier needs besides the proof
+
         def run(task):
             kind, i, ch = task
             L = self.layers[i]
