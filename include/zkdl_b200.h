@@ -32,6 +32,9 @@ enum { ZKDL_OK = 0, ZKDL_ERR_DIM = 1, ZKDL_ERR_CUDA = 2, ZKDL_ERR_ARG = 3, ZKDL_
 
 const char* zkdl_last_error(void);
 int zkdl_version(void);
+/* Pre-sizes the scratch arenas of `stream` (and of the calling thread's side streams) so that the first proof does not
+ * pay for cudaMalloc.  Optional: arenas also grow on demand and are warm after the first call. */
+int zkdl_scratch_reserve(size_t bytes, void* stream);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t zkdl_launch_count(void);
 

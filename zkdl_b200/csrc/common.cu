@@ -70,6 +70,12 @@ int scratch_free(void* p, cudaStream_t s) {
   }
   return ZK_OK;
 }
+static int reserve_one(cudaStream_t s, size_t bytes) {
+  void* p = nullptr;
+  int rc = scratch_alloc(&p, bytes, s);          // grows the arena to one block of at least `bytes` ...
+  if (rc) return rc;
+  return scratch_free(p, s);                     // ... and releases it (consolidating if it had several blocks)
+}
 SideStream& side_stream(int idx) {
   static thread_local SideStream pool[4];
   return pool[idx & 3];
@@ -101,6 +107,17 @@ int num_sms() {
 }  // namespace zk
 
 extern "C" {
+int zkdl_scratch_reserve(size_t bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = zk::reserve_one(st, bytes);
+  for (int i = 0; i < 3 && !rc; ++i) {           // the side streams this host thread forks sub-proofs onto
+    zk::SideStream& ss = zk::side_stream(i);
+    if ((rc = ss.fork(st))) break;
+    rc = zk::reserve_one(ss.stream, bytes / 2);
+    if (!rc) rc = ss.join(st);
+  }
+  return rc;
+}
 const char* zkdl_last_error(void) { return zk::g_err; }
 int zkdl_version(void) { return 100; }
 uint64_t zkdl_launch_count(void) { return zk::g_launches.load(); }

@@ -11,6 +11,7 @@
 // O(log n) extra launches per round.  Multilinear evaluation folds three variables per pass.  Once a table has
 // <= TAIL_N entries a single-CTA kernel finishes all remaining rounds without further launches.
 #include <atomic>
+#include <stdlib.h>
 #include "common.cuh"
 #include "fr_device.cuh"
 #include "../../include/zkdl_b200.h"
@@ -431,8 +432,11 @@ static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k,
     for (int r = 0; r < R; ++r) out_rows = (out_rows + 1) / 2;
     Fr* dst = bufs[which];
     size_t total = out_rows * w;
-    unsigned grid = stream_grid(total, THREADS);
-    if (R == 3) ZK_LAUNCH(k_fr_fold_multi<3><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
+    static const int fold_block = getenv("ZKDL_FOLD_BLOCK") ? atoi(getenv("ZKDL_FOLD_BLOCK")) : 128;     // tuning knob
+    static const int fold_cap = getenv("ZKDL_FOLD_CAP") ? atoi(getenv("ZKDL_FOLD_CAP")) : 16;
+    size_t blocks = (total + fold_block - 1) / fold_block, capb = (size_t)num_sms() * fold_cap;
+    unsigned grid = (unsigned)(blocks < capb ? (blocks ? blocks : 1) : capb);
+    if (R == 3) ZK_LAUNCH(k_fr_fold_multi<3><<<grid, fold_block, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     else if (R == 2) ZK_LAUNCH(k_fr_fold_multi<2><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     else ZK_LAUNCH(k_fr_fold_multi<1><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     cur = dst; cur_n = total; rows = out_rows; which ^= 1; j += R;

@@ -164,9 +164,10 @@ G1TensorAffine G1TensorAffine::operator-() const {                              
 }
 
 // ------------------------------------------------------------------------------------------------ G1TensorJacobian
-G1TensorJacobian::G1TensorJacobian(const G1TensorJacobian& t) : G1Tensor(t.size), gpu_data(dev_alloc<G1Jacobian_t>(t.size)) {
+G1TensorJacobian::G1TensorJacobian(const G1TensorJacobian& t) : G1Tensor(t.size), gpu_data(dev_alloc<G1Jacobian_t>(t.size)), table_(t.table_) {
   cuda_check(cudaMemcpy(gpu_data, t.gpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyDeviceToDevice));
 }
+G1TensorJacobian::TableHolder::~TableHolder() { if (t) { cudaDeviceSynchronize(); zkdl_g1_table_destroy(t); } }
 G1TensorJacobian::G1TensorJacobian(uint size) : G1Tensor(size), gpu_data(dev_alloc<G1Jacobian_t>(size)) {}
 G1TensorJacobian::G1TensorJacobian(uint size, const G1Jacobian_t& g) : G1Tensor(size), gpu_data(dev_alloc<G1Jacobian_t>(size)) {
   vector<G1Jacobian_t> h(size, g);
@@ -179,10 +180,14 @@ G1TensorJacobian::G1TensorJacobian(const G1TensorAffine& a) : G1Tensor(a.size), 
   check(zkdl_g1_affine_to_jacobian(a.gpu_data, gpu_data, size, 0)); sync();
 }
 G1TensorJacobian::~G1TensorJacobian() { invalidate_table(); cudaFree(gpu_data); gpu_data = nullptr; }
-void G1TensorJacobian::invalidate_table() const { if (table_) { cudaDeviceSynchronize(); zkdl_g1_table_destroy(table_); table_ = nullptr; } }
+void G1TensorJacobian::invalidate_table() const { table_.reset(); }
 const zkdl_g1_table* G1TensorJacobian::table() const {
-  if (!table_) { check(zkdl_g1_table_create(gpu_data, size, 0, 1, &table_, 0)); sync(); }
-  return table_;
+  if (!table_) {
+    auto h = std::make_shared<TableHolder>();
+    check(zkdl_g1_table_create(gpu_data, size, 0, 1, &h->t, 0)); sync();
+    table_ = h;
+  }
+  return table_->t;
 }
 G1Jacobian_t G1TensorJacobian::operator()(uint idx) const {
   G1Jacobian_t out; cuda_check(cudaMemcpy(&out, gpu_data + idx, sizeof(G1Jacobian_t), cudaMemcpyDeviceToHost)); return out;
@@ -317,6 +322,7 @@ void Fr_bin_sc(const FrTensor& a, vector<Fr_t>::const_iterator u_begin, vector<F
 zkFC::zkFC(uint input_size, uint output_size, const FrTensor& t, const Commitment& c)
     : weights(t), com(c.commit(t)), inputSize(input_size), outputSize(output_size) {        // zkfc.cu:102-104
   if (t.size != input_size * output_size) throw std::runtime_error("Incompatible dimensions");
+  com.table();                       // fixed-base tables of the commitment vector: setup work, like commit() itself
 }
 zkFC zkFC::from_float_gpu_ptr(uint input_size, uint output_size, float* float_gpu_ptr, const Commitment& generators) {   // zkfc.cu:90-100
   uint I = 1u << ceilLog2(input_size), O = 1u << ceilLog2(output_size);

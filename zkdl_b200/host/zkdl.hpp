@@ -19,6 +19,7 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <memory>
 #include <random>
 #include <stdexcept>
 #include <utility>
@@ -140,11 +141,13 @@ class G1TensorJacobian : public G1Tensor {
   G1TensorJacobian operator*(const FrTensor&) const;
   G1TensorJacobian& operator*=(const FrTensor&);
   G1Jacobian_t operator()(const std::vector<Fr_t>& u) const;
-  // fixed-base window tables of these points, built on first use and dropped whenever the points change
+  // fixed-base window tables of these points: built on first use, shared by copies of the tensor (same points), and
+  // dropped by an object whenever ITS points change
   const zkdl_g1_table* table() const;
   void invalidate_table() const;
  private:
-  mutable zkdl_g1_table* table_ = nullptr;
+  struct TableHolder { zkdl_g1_table* t = nullptr; ~TableHolder(); };
+  mutable std::shared_ptr<TableHolder> table_;
   G1TensorJacobian binary(int op, const void* b, size_t nb) const;
   G1TensorJacobian& binary_inplace(int op, const void* b, size_t nb);
 };
