@@ -14,10 +14,33 @@ const G1Jacobian_t G1Jacobian_generator = {G1_generator_x_mont, G1_generator_y_m
 const Fr_t Fr_ONE_mont = {{4294967294u, 1u, 215042u, 1485092858u, 3971764213u, 2576109551u, 2898593135u, 405057881u}};
 const Fr_t Fr_ZERO = {{0, 0, 0, 0, 0, 0, 0, 0}};
 
+// ------------------------------------------------------------------------------------------------ streams / memory
+static thread_local cudaStream_t t_stream = 0;
+cudaStream_t zkdl_host::cur_stream() { return t_stream; }
+void zkdl_host::set_thread_stream(cudaStream_t s) { t_stream = s; }
+void* zkdl_host::dev_alloc_bytes(size_t bytes) {
+  void* p = nullptr;
+  if (t_stream == 0) cuda_check(cudaMalloc(&p, bytes));                          // the reference's behaviour (fr-tensor.cu:92-95)
+  else cuda_check(cudaMallocAsync(&p, bytes, t_stream));
+  return p;
+}
+void zkdl_host::dev_free(void* p) {
+  if (!p) return;
+  if (t_stream == 0) cudaFree(p); else cudaFreeAsync(p, t_stream);
+}
+void zkdl_host::copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+  if (t_stream == 0) { cuda_check(cudaMemcpy(dst, src, bytes, kind)); return; }
+  cuda_check(cudaMemcpyAsync(dst, src, bytes, kind, t_stream));
+  cuda_check(cudaStreamSynchronize(t_stream));
+}
+
 // ------------------------------------------------------------------------------------------------ challenge seeds
 static std::atomic<uint32_t> g_seed_base{0}, g_seed_ctr{0};
+static thread_local uint32_t t_seed_base = 0, t_seed_ctr = 0;
 void set_challenge_seed(uint32_t seed) { g_seed_base = seed; g_seed_ctr = 0; }
+void set_thread_challenge_seed(uint32_t seed) { t_seed_base = seed; t_seed_ctr = 0; }
 uint32_t zkdl_host::next_challenge_seed() {
+  if (t_seed_base) return t_seed_base + t_seed_ctr++;
   if (g_seed_base.load() == 0) { std::random_device rd; return rd(); }          // proof.cu:5-6
   return g_seed_base.load() + g_seed_ctr.fetch_add(1);
 }
@@ -37,7 +60,7 @@ std::ostream& operator<<(std::ostream& os, const G1Affine_t& g) { return os << "
 std::ostream& operator<<(std::ostream& os, const G1Jacobian_t& g) { return os << "(" << g.x << ", " << g.y << ", " << g.z << ")"; }
 std::ostream& operator<<(std::ostream& os, const FrTensor& A) {                   // fr-tensor.cu:445-451 (one bulk copy instead of size copies)
   vector<Fr_t> h(A.size);
-  cuda_check(cudaMemcpy(h.data(), A.gpu_data, sizeof(Fr_t) * A.size, cudaMemcpyDeviceToHost));
+  copy(h.data(), A.gpu_data, sizeof(Fr_t) * A.size, cudaMemcpyDeviceToHost);
   os << '[';
   for (uint i = 0; i + 1 < A.size; ++i) os << h[i] << '\n';
   if (A.size) os << h[A.size - 1];
@@ -47,77 +70,78 @@ std::ostream& operator<<(std::ostream& os, const FrTensor& A) {                 
 // ------------------------------------------------------------------------------------------------ FrTensor
 FrTensor::FrTensor(uint size) : gpu_data(dev_alloc<Fr_t>(size)), size(size) {}
 FrTensor::FrTensor(uint size, const Fr_t* cpu_data) : gpu_data(dev_alloc<Fr_t>(size)), size(size) {
-  cuda_check(cudaMemcpy(gpu_data, cpu_data, sizeof(Fr_t) * size, cudaMemcpyHostToDevice));
+  copy(gpu_data, cpu_data, sizeof(Fr_t) * size, cudaMemcpyHostToDevice);
 }
 FrTensor::FrTensor(const FrTensor& t) : gpu_data(dev_alloc<Fr_t>(t.size)), size(t.size) {
-  cuda_check(cudaMemcpy(gpu_data, t.gpu_data, sizeof(Fr_t) * size, cudaMemcpyDeviceToDevice));
+  copy(gpu_data, t.gpu_data, sizeof(Fr_t) * size, cudaMemcpyDeviceToDevice);
 }
-FrTensor::~FrTensor() { cudaFree(gpu_data); gpu_data = nullptr; }
+FrTensor::~FrTensor() { dev_free(gpu_data); gpu_data = nullptr; }
 Fr_t FrTensor::operator()(uint idx) const {
-  Fr_t out; cuda_check(cudaMemcpy(&out, gpu_data + idx, sizeof(Fr_t), cudaMemcpyDeviceToHost)); return out;
+  Fr_t out; copy(&out, gpu_data + idx, sizeof(Fr_t), cudaMemcpyDeviceToHost); return out;
 }
 static FrTensor fr_binary(int op, const FrTensor& a, const FrTensor& b) {
   if (a.size != b.size) throw std::runtime_error("Incompatible dimensions");
-  FrTensor out(a.size); check(zkdl_fr_elementwise(op, a.gpu_data, b.gpu_data, out.gpu_data, a.size, 0)); sync(); return out;
+  FrTensor out(a.size); check(zkdl_fr_elementwise(op, a.gpu_data, b.gpu_data, out.gpu_data, a.size, st())); sync(); return out;
 }
 static FrTensor fr_bcast(int op, const FrTensor& a, const Fr_t& x) {
-  FrTensor out(a.size); check(zkdl_fr_broadcast(op, a.gpu_data, &x, out.gpu_data, a.size, 0)); sync(); return out;
+  FrTensor out(a.size); check(zkdl_fr_broadcast(op, a.gpu_data, &x, out.gpu_data, a.size, st())); sync(); return out;
 }
 FrTensor FrTensor::operator+(const FrTensor& t) const { return fr_binary(ZKDL_OP_ADD, *this, t); }
 FrTensor FrTensor::operator+(const Fr_t& x) const { return fr_bcast(ZKDL_OP_ADD, *this, x); }
 FrTensor& FrTensor::operator+=(const FrTensor& t) {
   if (size != t.size) throw std::runtime_error("Incompatible dimensions");
-  check(zkdl_fr_elementwise(ZKDL_OP_ADD, gpu_data, t.gpu_data, gpu_data, size, 0)); sync(); return *this;
+  check(zkdl_fr_elementwise(ZKDL_OP_ADD, gpu_data, t.gpu_data, gpu_data, size, st())); sync(); return *this;
 }
-FrTensor& FrTensor::operator+=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_ADD, gpu_data, &x, gpu_data, size, 0)); sync(); return *this; }
-FrTensor FrTensor::operator-() const { FrTensor out(size); check(zkdl_fr_elementwise(ZKDL_OP_NEG, gpu_data, nullptr, out.gpu_data, size, 0)); sync(); return out; }
+FrTensor& FrTensor::operator+=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_ADD, gpu_data, &x, gpu_data, size, st())); sync(); return *this; }
+FrTensor FrTensor::operator-() const { FrTensor out(size); check(zkdl_fr_elementwise(ZKDL_OP_NEG, gpu_data, nullptr, out.gpu_data, size, st())); sync(); return out; }
 FrTensor FrTensor::operator-(const FrTensor& t) const { return fr_binary(ZKDL_OP_SUB, *this, t); }
 FrTensor FrTensor::operator-(const Fr_t& x) const { return fr_bcast(ZKDL_OP_SUB, *this, x); }
 FrTensor& FrTensor::operator-=(const FrTensor& t) {
   if (size != t.size) throw std::runtime_error("Incompatible dimensions");
-  check(zkdl_fr_elementwise(ZKDL_OP_SUB, gpu_data, t.gpu_data, gpu_data, size, 0)); sync(); return *this;
+  check(zkdl_fr_elementwise(ZKDL_OP_SUB, gpu_data, t.gpu_data, gpu_data, size, st())); sync(); return *this;
 }
-FrTensor& FrTensor::operator-=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_SUB, gpu_data, &x, gpu_data, size, 0)); sync(); return *this; }
-FrTensor& FrTensor::mont() { check(zkdl_fr_elementwise(ZKDL_OP_MONT, gpu_data, nullptr, gpu_data, size, 0)); sync(); return *this; }
-FrTensor& FrTensor::unmont() { check(zkdl_fr_elementwise(ZKDL_OP_UNMONT, gpu_data, nullptr, gpu_data, size, 0)); sync(); return *this; }
+FrTensor& FrTensor::operator-=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_SUB, gpu_data, &x, gpu_data, size, st())); sync(); return *this; }
+FrTensor& FrTensor::mont() { check(zkdl_fr_elementwise(ZKDL_OP_MONT, gpu_data, nullptr, gpu_data, size, st())); sync(); return *this; }
+FrTensor& FrTensor::unmont() { check(zkdl_fr_elementwise(ZKDL_OP_UNMONT, gpu_data, nullptr, gpu_data, size, st())); sync(); return *this; }
 FrTensor FrTensor::operator*(const FrTensor& t) const { return fr_binary(ZKDL_OP_MUL, *this, t); }
 FrTensor FrTensor::operator*(const Fr_t& x) const { return fr_bcast(ZKDL_OP_MUL, *this, x); }
 FrTensor& FrTensor::operator*=(const FrTensor& t) {
   if (size != t.size) throw std::runtime_error("Incompatible dimensions");
-  check(zkdl_fr_elementwise(ZKDL_OP_MUL, gpu_data, t.gpu_data, gpu_data, size, 0)); sync(); return *this;
+  check(zkdl_fr_elementwise(ZKDL_OP_MUL, gpu_data, t.gpu_data, gpu_data, size, st())); sync(); return *this;
 }
-FrTensor& FrTensor::operator*=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_MUL, gpu_data, &x, gpu_data, size, 0)); sync(); return *this; }
+FrTensor& FrTensor::operator*=(const Fr_t& x) { check(zkdl_fr_broadcast(ZKDL_OP_MUL, gpu_data, &x, gpu_data, size, st())); sync(); return *this; }
 Fr_t FrTensor::sum() const {
-  FrTensor out(1); check(zkdl_fr_sum(gpu_data, size, out.gpu_data, 0)); sync(); return out(0);
+  FrTensor out(1); check(zkdl_fr_sum(gpu_data, size, out.gpu_data, st())); sync(); return out(0);
 }
 Fr_t FrTensor::operator()(const vector<Fr_t>& u) const {
-  FrTensor out(1); check(zkdl_fr_me(gpu_data, size, u.data(), u.size(), out.gpu_data, 0)); sync(); return out(0);
+  FrTensor out(1); check(zkdl_fr_me(gpu_data, size, u.data(), u.size(), out.gpu_data, st())); sync(); return out(0);
 }
 Fr_t Fr_me(const FrTensor& t, vector<Fr_t>::const_iterator begin, vector<Fr_t>::const_iterator end) {
   // the reference's Fr_me applies end-begin folds without the size guard of operator()(u) (fr-tensor.cu:411-418)
   size_t k = end - begin;
   if (k == 0) return t(0);
   FrTensor out((uint)zkdl_partial_me_size(t.size, k, 1));
-  check(zkdl_fr_partial_me(t.gpu_data, t.size, &*begin, k, 1, out.gpu_data, 0)); sync();
+  check(zkdl_fr_partial_me(t.gpu_data, t.size, &*begin, k, 1, out.gpu_data, st())); sync();
   return out(0);
 }
 std::pair<FrTensor, FrTensor> FrTensor::split(uint window_size) const {           // fr-tensor.cu:376-397
   if (window_size < 1 || window_size >= size) throw std::runtime_error("Invalid window size.");
   uint out_size = (size + 1) / 2;
   std::pair<FrTensor, FrTensor> out{out_size, out_size};
-  cuda_check(cudaMemset(out.first.gpu_data, 0, sizeof(Fr_t) * out_size));
-  cuda_check(cudaMemset(out.second.gpu_data, 0, sizeof(Fr_t) * out_size));
+  cuda_check(cudaMemsetAsync(out.first.gpu_data, 0, sizeof(Fr_t) * out_size, cur_stream()));
+  cuda_check(cudaMemsetAsync(out.second.gpu_data, 0, sizeof(Fr_t) * out_size, cur_stream()));
+  sync();
   for (uint wid = 0; (size_t)wid * window_size < out_size; ++wid) {                // window-wise device copies
     size_t dst = (size_t)wid * window_size, n0 = std::min<size_t>(window_size, out_size - dst);
     size_t s0 = 2 * (size_t)wid * window_size, s1 = s0 + window_size;
-    if (s0 < size) cuda_check(cudaMemcpy(out.first.gpu_data + dst, gpu_data + s0, sizeof(Fr_t) * std::min<size_t>(n0, size - s0), cudaMemcpyDeviceToDevice));
-    if (s1 < size) cuda_check(cudaMemcpy(out.second.gpu_data + dst, gpu_data + s1, sizeof(Fr_t) * std::min<size_t>(n0, size - s1), cudaMemcpyDeviceToDevice));
+    if (s0 < size) copy(out.first.gpu_data + dst, gpu_data + s0, sizeof(Fr_t) * std::min<size_t>(n0, size - s0), cudaMemcpyDeviceToDevice);
+    if (s1 < size) copy(out.second.gpu_data + dst, gpu_data + s1, sizeof(Fr_t) * std::min<size_t>(n0, size - s1), cudaMemcpyDeviceToDevice);
   }
   return out;
 }
 FrTensor FrTensor::partial_me(vector<Fr_t> u, uint window_size) const {
   FrTensor out((uint)zkdl_partial_me_size(size, u.size(), window_size));
-  check(zkdl_fr_partial_me(gpu_data, size, u.data(), u.size(), window_size, out.gpu_data, 0)); sync();
+  check(zkdl_fr_partial_me(gpu_data, size, u.data(), u.size(), window_size, out.gpu_data, st())); sync();
   return out;
 }
 FrTensor Fr_partial_me(const FrTensor& t, vector<Fr_t>::const_iterator begin, vector<Fr_t>::const_iterator end, uint window_size) {
@@ -140,67 +164,67 @@ FrTensor FrTensor::random(uint size) {                                          
 
 // ------------------------------------------------------------------------------------------------ G1TensorAffine
 G1TensorAffine::G1TensorAffine(const G1TensorAffine& t) : G1Tensor(t.size), gpu_data(dev_alloc<G1Affine_t>(t.size)) {
-  cuda_check(cudaMemcpy(gpu_data, t.gpu_data, sizeof(G1Affine_t) * size, cudaMemcpyDeviceToDevice));
+  copy(gpu_data, t.gpu_data, sizeof(G1Affine_t) * size, cudaMemcpyDeviceToDevice);
 }
 G1TensorAffine::G1TensorAffine(uint size) : G1Tensor(size), gpu_data(dev_alloc<G1Affine_t>(size)) {}
 G1TensorAffine::G1TensorAffine(uint size, const G1Affine_t& g) : G1Tensor(size), gpu_data(dev_alloc<G1Affine_t>(size)) {
   vector<G1Affine_t> h(size, g);
-  cuda_check(cudaMemcpy(gpu_data, h.data(), sizeof(G1Affine_t) * size, cudaMemcpyHostToDevice));
+  copy(gpu_data, h.data(), sizeof(G1Affine_t) * size, cudaMemcpyHostToDevice);
 }
 G1TensorAffine::G1TensorAffine(uint size, const G1Affine_t* cpu_data) : G1Tensor(size), gpu_data(dev_alloc<G1Affine_t>(size)) {
-  cuda_check(cudaMemcpy(gpu_data, cpu_data, sizeof(G1Affine_t) * size, cudaMemcpyHostToDevice));
+  copy(gpu_data, cpu_data, sizeof(G1Affine_t) * size, cudaMemcpyHostToDevice);
 }
-G1TensorAffine::~G1TensorAffine() { cudaFree(gpu_data); gpu_data = nullptr; }
+G1TensorAffine::~G1TensorAffine() { dev_free(gpu_data); gpu_data = nullptr; }
 G1Affine_t G1TensorAffine::operator()(uint idx) const {
-  G1Affine_t out; cuda_check(cudaMemcpy(&out, gpu_data + idx, sizeof(G1Affine_t), cudaMemcpyDeviceToHost)); return out;
+  G1Affine_t out; copy(&out, gpu_data + idx, sizeof(G1Affine_t), cudaMemcpyDeviceToHost); return out;
 }
 G1TensorAffine G1TensorAffine::operator-() const {                                  // y -> p - y via the Jacobian kernel
   G1TensorJacobian j(*this);
   G1TensorJacobian nj = -j;
   vector<G1Jacobian_t> h(size); vector<G1Affine_t> a(size);
-  cuda_check(cudaMemcpy(h.data(), nj.gpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyDeviceToHost));
+  copy(h.data(), nj.gpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyDeviceToHost);
   for (uint i = 0; i < size; ++i) { a[i].x = h[i].x; a[i].y = h[i].y; }
   return G1TensorAffine(size, a.data());
 }
 
 // ------------------------------------------------------------------------------------------------ G1TensorJacobian
 G1TensorJacobian::G1TensorJacobian(const G1TensorJacobian& t) : G1Tensor(t.size), gpu_data(dev_alloc<G1Jacobian_t>(t.size)), table_(t.table_) {
-  cuda_check(cudaMemcpy(gpu_data, t.gpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyDeviceToDevice));
+  copy(gpu_data, t.gpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyDeviceToDevice);
 }
 G1TensorJacobian::TableHolder::~TableHolder() { if (t) { cudaDeviceSynchronize(); zkdl_g1_table_destroy(t); } }
 G1TensorJacobian::G1TensorJacobian(uint size) : G1Tensor(size), gpu_data(dev_alloc<G1Jacobian_t>(size)) {}
 G1TensorJacobian::G1TensorJacobian(uint size, const G1Jacobian_t& g) : G1Tensor(size), gpu_data(dev_alloc<G1Jacobian_t>(size)) {
   vector<G1Jacobian_t> h(size, g);
-  cuda_check(cudaMemcpy(gpu_data, h.data(), sizeof(G1Jacobian_t) * size, cudaMemcpyHostToDevice));
+  copy(gpu_data, h.data(), sizeof(G1Jacobian_t) * size, cudaMemcpyHostToDevice);
 }
 G1TensorJacobian::G1TensorJacobian(uint size, const G1Jacobian_t* cpu_data) : G1Tensor(size), gpu_data(dev_alloc<G1Jacobian_t>(size)) {
-  cuda_check(cudaMemcpy(gpu_data, cpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyHostToDevice));
+  copy(gpu_data, cpu_data, sizeof(G1Jacobian_t) * size, cudaMemcpyHostToDevice);
 }
 G1TensorJacobian::G1TensorJacobian(const G1TensorAffine& a) : G1Tensor(a.size), gpu_data(dev_alloc<G1Jacobian_t>(a.size)) {
-  check(zkdl_g1_affine_to_jacobian(a.gpu_data, gpu_data, size, 0)); sync();
+  check(zkdl_g1_affine_to_jacobian(a.gpu_data, gpu_data, size, st())); sync();
 }
-G1TensorJacobian::~G1TensorJacobian() { invalidate_table(); cudaFree(gpu_data); gpu_data = nullptr; }
+G1TensorJacobian::~G1TensorJacobian() { invalidate_table(); dev_free(gpu_data); gpu_data = nullptr; }
 void G1TensorJacobian::invalidate_table() const { table_.reset(); }
 const zkdl_g1_table* G1TensorJacobian::table() const {
   if (!table_) {
     auto h = std::make_shared<TableHolder>();
-    check(zkdl_g1_table_create(gpu_data, size, 0, 1, &h->t, 0)); sync();
+    check(zkdl_g1_table_create(gpu_data, size, 0, 1, &h->t, st())); sync();
     table_ = h;
   }
   return table_->t;
 }
 G1Jacobian_t G1TensorJacobian::operator()(uint idx) const {
-  G1Jacobian_t out; cuda_check(cudaMemcpy(&out, gpu_data + idx, sizeof(G1Jacobian_t), cudaMemcpyDeviceToHost)); return out;
+  G1Jacobian_t out; copy(&out, gpu_data + idx, sizeof(G1Jacobian_t), cudaMemcpyDeviceToHost); return out;
 }
 G1TensorJacobian G1TensorJacobian::binary(int op, const void* b, size_t nb) const {
-  G1TensorJacobian out(size); check(zkdl_g1_elementwise(op, gpu_data, b, nb, out.gpu_data, size, 0)); sync(); return out;
+  G1TensorJacobian out(size); check(zkdl_g1_elementwise(op, gpu_data, b, nb, out.gpu_data, size, st())); sync(); return out;
 }
 G1TensorJacobian& G1TensorJacobian::binary_inplace(int op, const void* b, size_t nb) {
   invalidate_table();
-  check(zkdl_g1_elementwise(op, gpu_data, b, nb, gpu_data, size, 0)); sync(); return *this;
+  check(zkdl_g1_elementwise(op, gpu_data, b, nb, gpu_data, size, st())); sync(); return *this;
 }
 template <class T> struct DevOne {     // a single point uploaded for the broadcast forms
-  T* p; DevOne(const T& v) : p(dev_alloc<T>(1)) { cuda_check(cudaMemcpy(p, &v, sizeof(T), cudaMemcpyHostToDevice)); } ~DevOne() { cudaFree(p); }
+  T* p; DevOne(const T& v) : p(dev_alloc<T>(1)) { copy(p, &v, sizeof(T), cudaMemcpyHostToDevice); } ~DevOne() { dev_free(p); }
 };
 static void same(uint a, uint b) { if (a != b) throw std::runtime_error("Incompatible dimensions"); }
 G1TensorJacobian G1TensorJacobian::operator-() const { return binary(ZKDL_G1_NEG, nullptr, 0); }
@@ -221,19 +245,19 @@ G1TensorJacobian& G1TensorJacobian::operator-=(const G1TensorAffine& t) { same(s
 G1TensorJacobian& G1TensorJacobian::operator-=(const G1Jacobian_t& x) { DevOne<G1Jacobian_t> d(x); return binary_inplace(ZKDL_G1_SUB, d.p, 1); }
 G1TensorJacobian& G1TensorJacobian::operator-=(const G1Affine_t& x) { DevOne<G1Affine_t> d(x); return binary_inplace(ZKDL_G1_MSUB, d.p, 1); }
 G1Jacobian_t G1TensorJacobian::sum() const {
-  G1TensorJacobian out(1); check(zkdl_g1_sum(gpu_data, size, out.gpu_data, 0)); sync(); return out(0);
+  G1TensorJacobian out(1); check(zkdl_g1_sum(gpu_data, size, out.gpu_data, st())); sync(); return out(0);
 }
 G1TensorJacobian G1TensorJacobian::operator*(const FrTensor& s) const {             // g1-tensor.cu:447-454
   if (s.size % size != 0) throw std::runtime_error("Incompatible dimensions");
-  G1TensorJacobian out(s.size); check(zkdl_g1_mul(gpu_data, size, s.gpu_data, s.size, out.gpu_data, 0)); sync(); return out;
+  G1TensorJacobian out(s.size); check(zkdl_g1_mul(gpu_data, size, s.gpu_data, s.size, out.gpu_data, st())); sync(); return out;
 }
 G1TensorJacobian& G1TensorJacobian::operator*=(const FrTensor& s) {                 // g1-tensor.cu:456-461
   if (size != s.size) throw std::runtime_error("Incompatible dimensions 01");
   invalidate_table();
-  check(zkdl_g1_mul(gpu_data, size, s.gpu_data, s.size, gpu_data, 0)); sync(); return *this;
+  check(zkdl_g1_mul(gpu_data, size, s.gpu_data, s.size, gpu_data, st())); sync(); return *this;
 }
 G1Jacobian_t G1TensorJacobian::operator()(const vector<Fr_t>& u) const {
-  G1TensorJacobian out(1); check(zkdl_g1_me(gpu_data, size, u.data(), u.size(), out.gpu_data, 0)); sync(); return out(0);
+  G1TensorJacobian out(1); check(zkdl_g1_me(gpu_data, size, u.data(), u.size(), out.gpu_data, st())); sync(); return out(0);
 }
 G1Jacobian_t G1_me(const G1TensorJacobian& t, vector<Fr_t>::const_iterator begin, vector<Fr_t>::const_iterator end) {
   return t(vector<Fr_t>(begin, end));
@@ -243,7 +267,7 @@ G1Jacobian_t G1_me(const G1TensorJacobian& t, vector<Fr_t>::const_iterator begin
 G1TensorJacobian Commitment::commit(const FrTensor& t) const {                       // commitment.cu:29-41 (intended semantics)
   if (t.size % size != 0) throw std::runtime_error("Incompatible dimensions");
   G1TensorJacobian out(t.size / size);
-  check(zkdl_commit(table(), t.gpu_data, t.size, out.gpu_data, 0)); sync();
+  check(zkdl_commit(table(), t.gpu_data, t.size, out.gpu_data, st())); sync();
   return out;
 }
 Fr_t Commitment::me_open(const FrTensor& t, const Commitment& generators, vector<Fr_t>::const_iterator begin, vector<Fr_t>::const_iterator end,
@@ -251,9 +275,9 @@ Fr_t Commitment::me_open(const FrTensor& t, const Commitment& generators, vector
   if (t.size != generators.size) throw std::runtime_error("Incompatible dimensions");
   size_t k = end - begin;
   G1TensorJacobian pr((uint)(3 * k + 1)); FrTensor ret(1);
-  check(zkdl_me_open(generators.table(), t.gpu_data, t.size, k ? &*begin : nullptr, k, pr.gpu_data, ret.gpu_data, 0)); sync();
+  check(zkdl_me_open(generators.table(), t.gpu_data, t.size, k ? &*begin : nullptr, k, pr.gpu_data, ret.gpu_data, st())); sync();
   vector<G1Jacobian_t> h(3 * k + 1);
-  cuda_check(cudaMemcpy(h.data(), pr.gpu_data, sizeof(G1Jacobian_t) * h.size(), cudaMemcpyDeviceToHost));
+  copy(h.data(), pr.gpu_data, sizeof(G1Jacobian_t) * h.size(), cudaMemcpyDeviceToHost);
   proof.insert(proof.end(), h.begin(), h.end());
   return ret(0);
 }
@@ -262,9 +286,9 @@ Fr_t Commitment::open_with_proof(const FrTensor& t, const G1TensorJacobian& c, c
   if (u.size() < khi) throw std::runtime_error("Incompatible dimensions");
   size_t klo = u.size() - khi;
   G1TensorJacobian pr((uint)(3 * klo + 2)); FrTensor ret(1);
-  check(zkdl_open(table(), c.table(), t.gpu_data, t.size, u.data(), u.size(), pr.gpu_data, pr.gpu_data + 1, ret.gpu_data, 0)); sync();
+  check(zkdl_open(table(), c.table(), t.gpu_data, t.size, u.data(), u.size(), pr.gpu_data, pr.gpu_data + 1, ret.gpu_data, st())); sync();
   vector<G1Jacobian_t> h(3 * klo + 2);
-  cuda_check(cudaMemcpy(h.data(), pr.gpu_data, sizeof(G1Jacobian_t) * h.size(), cudaMemcpyDeviceToHost));
+  copy(h.data(), pr.gpu_data, sizeof(G1Jacobian_t) * h.size(), cudaMemcpyDeviceToHost);
   proof.insert(proof.end(), h.begin(), h.end());
   return ret(0);
 }
@@ -283,26 +307,26 @@ uint ceilLog2(uint num) { return zkdl_ceil_log2(num); }
 
 static vector<Fr_t> download(const FrTensor& t) {
   vector<Fr_t> h(t.size);
-  cuda_check(cudaMemcpy(h.data(), t.gpu_data, sizeof(Fr_t) * t.size, cudaMemcpyDeviceToHost));
+  copy(h.data(), t.gpu_data, sizeof(Fr_t) * t.size, cudaMemcpyDeviceToHost);
   return h;
 }
 vector<Fr_t> inner_product_sumcheck(const FrTensor& a, const FrTensor& b, vector<Fr_t> u) {
   if (a.size != b.size) throw std::runtime_error("Incompatible dimensions");
   FrTensor proof((uint)(3 * u.size() + 2));
-  check(zkdl_ip_sumcheck(a.gpu_data, b.gpu_data, a.size, u.data(), u.size(), proof.gpu_data, 0)); sync();
+  check(zkdl_ip_sumcheck(a.gpu_data, b.gpu_data, a.size, u.data(), u.size(), proof.gpu_data, st())); sync();
   return download(proof);
 }
 vector<Fr_t> hadamard_product_sumcheck(const FrTensor& a, const FrTensor& b, vector<Fr_t> u, vector<Fr_t> v) {
   if (u.size() != v.size()) throw std::runtime_error("Incompatible dimensions 1");
   if (a.size != b.size) throw std::runtime_error("Incompatible dimensions 2");
   FrTensor proof((uint)(3 * u.size() + 2));
-  check(zkdl_hp_sumcheck(a.gpu_data, b.gpu_data, a.size, u.data(), v.data(), u.size(), proof.gpu_data, 0)); sync();
+  check(zkdl_hp_sumcheck(a.gpu_data, b.gpu_data, a.size, u.data(), v.data(), u.size(), proof.gpu_data, st())); sync();
   return download(proof);
 }
 vector<Fr_t> binary_sumcheck(const FrTensor& a, vector<Fr_t> u, vector<Fr_t> v) {
   if (u.size() != v.size()) throw std::runtime_error("Incompatible dimensions");
   FrTensor proof((uint)(3 * u.size() + 1));
-  check(zkdl_bin_sumcheck(a.gpu_data, a.size, u.data(), v.data(), u.size(), proof.gpu_data, 0)); sync();
+  check(zkdl_bin_sumcheck(a.gpu_data, a.size, u.data(), v.data(), u.size(), proof.gpu_data, st())); sync();
   return download(proof);
 }
 // iterator forms (the reference's recursion entry points): same element order, no size guards beyond a.size == b.size
@@ -327,20 +351,20 @@ zkFC::zkFC(uint input_size, uint output_size, const FrTensor& t, const Commitmen
 zkFC zkFC::from_float_gpu_ptr(uint input_size, uint output_size, float* float_gpu_ptr, const Commitment& generators) {   // zkfc.cu:90-100
   uint I = 1u << ceilLog2(input_size), O = 1u << ceilLog2(output_size);
   FrTensor w(I * O);
-  check(zkdl_float_to_fr(float_gpu_ptr, w.gpu_data, input_size, I, output_size, O, 0)); sync();
+  check(zkdl_float_to_fr(float_gpu_ptr, w.gpu_data, input_size, I, output_size, O, st())); sync();
   return zkFC(I, O, w.mont(), generators);
 }
 FrTensor zkFC::load_float_gpu_input(uint batch_size, uint input_dim, float* input_ptr) {                                // zkfc.cu:106-115
   uint B = 1u << ceilLog2(batch_size), I = 1u << ceilLog2(input_dim);
   FrTensor t(B * I);
-  check(zkdl_float_to_fr(input_ptr, t.gpu_data, batch_size, B, input_dim, I, 0)); sync();
+  check(zkdl_float_to_fr(input_ptr, t.gpu_data, batch_size, B, input_dim, I, st())); sync();
   return t;
 }
 FrTensor zkFC::operator()(const FrTensor& X) const {                                                                    // zkfc.cu:117-126
   if (X.size % inputSize != 0) throw std::runtime_error("Incompatible dimensions");
   uint B = X.size / inputSize;
   FrTensor out(B * outputSize);
-  check(zkdl_fr_matmul(X.gpu_data, weights.gpu_data, out.gpu_data, B, inputSize, outputSize, 0)); sync();
+  check(zkdl_fr_matmul(X.gpu_data, weights.gpu_data, out.gpu_data, B, inputSize, outputSize, st())); sync();
   return out;
 }
 void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) const {                                  // zkfc.cu:128-145
@@ -353,31 +377,31 @@ void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) c
   zkdl_zkfc_proof_sizes(B, inputSize, outputSize, generators.size, &nfr, &ng1);
   FrTensor pfr((uint)nfr); G1TensorJacobian pg1((uint)ng1);
   check(zkdl_zkfc_prove(X.gpu_data, weights.gpu_data, Z.gpu_data, B, inputSize, outputSize, generators.table(), com.table(),
-                        u_bs.data(), u_in.data(), u_out.data(), pfr.gpu_data, pg1.gpu_data, 0));
+                        u_bs.data(), u_in.data(), u_out.data(), pfr.gpu_data, pg1.gpu_data, st()));
   sync();
   proof_fr_ = download(pfr);
   proof_g1_.resize(ng1);
-  cuda_check(cudaMemcpy(proof_g1_.data(), pg1.gpu_data, sizeof(G1Jacobian_t) * ng1, cudaMemcpyDeviceToHost));
+  copy(proof_g1_.data(), pg1.gpu_data, sizeof(G1Jacobian_t) * ng1, cudaMemcpyDeviceToHost);
 }
 
 // ------------------------------------------------------------------------------------------------ zkReLU
 bool zkReLU::materialize_tables = true;
 void zkReLU::reset_ptrs(uint size) {                                                                                    // zkrelu.cu:53-62
   delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; mag_bin_ptr = rem_bin_ptr = nullptr;
-  cudaFree(mag_packed_); cudaFree(rem_packed_);
+  dev_free(mag_packed_); dev_free(rem_packed_);
   sign_ptr = new FrTensor(size);
   mag_packed_ = dev_alloc<uint32_t>(size); rem_packed_ = dev_alloc<uint16_t>(size); n_ = size;
   if (materialize_tables) { mag_bin_ptr = new FrTensor(size * 32); rem_bin_ptr = new FrTensor(size * 16); }
 }
 zkReLU::~zkReLU() {
   delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; sign_ptr = mag_bin_ptr = rem_bin_ptr = nullptr;
-  cudaFree(mag_packed_); cudaFree(rem_packed_); mag_packed_ = nullptr; rem_packed_ = nullptr;
+  dev_free(mag_packed_); dev_free(rem_packed_); mag_packed_ = nullptr; rem_packed_ = nullptr;
 }
 FrTensor zkReLU::operator()(const FrTensor& X) {                                                                        // zkrelu.cu:44-51
   reset_ptrs(X.size);
   FrTensor out(X.size);
-  check(zkdl_relu_packed(X.gpu_data, out.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, nullptr, 0));
-  if (materialize_tables) check(zkdl_relu_expand(mag_packed_, rem_packed_, mag_bin_ptr->gpu_data, rem_bin_ptr->gpu_data, X.size, 0));
+  check(zkdl_relu_packed(X.gpu_data, out.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, nullptr, st()));
+  if (materialize_tables) check(zkdl_relu_expand(mag_packed_, rem_packed_, mag_bin_ptr->gpu_data, rem_bin_ptr->gpu_data, X.size, st()));
   sync();
   return out;
 }
@@ -389,7 +413,7 @@ void zkReLU::prove(const FrTensor& X, const FrTensor& Z) {                      
   auto u_hp = random_vec(L), v_hp = random_vec(L);
   FrTensor p((uint)zkdl_zkrelu_proof_size(X.size));
   check(zkdl_zkrelu_prove_packed(X.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, u_z.data(), v_z.data(), u_r.data(),
-                                 v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), p.gpu_data, 0));
+                                 v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), p.gpu_data, st()));
   sync();
   proof_ = download(p);
 }

@@ -39,12 +39,22 @@ inline void check(int rc) {
   throw std::runtime_error(std::string("zkdl_b200: ") + zkdl_last_error());
 }
 inline void cuda_check(cudaError_t e) { if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA: ") + cudaGetErrorString(e)); }
-inline void sync() { cuda_check(cudaStreamSynchronize(0)); }
-template <class T> T* dev_alloc(size_t n) { T* p = nullptr; cuda_check(cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1))); return p; }
+// Every shim operation runs on the calling thread's current stream (default: the legacy default stream, exactly like
+// the reference) and synchronises it before returning.  set_thread_stream() lets independent proofs run concurrently
+// from several host threads (demo.cpp proves the layers that way); memory then comes from the stream-ordered pool.
+cudaStream_t cur_stream();
+void set_thread_stream(cudaStream_t s);
+inline void* st() { return reinterpret_cast<void*>(cur_stream()); }
+inline void sync() { cuda_check(cudaStreamSynchronize(cur_stream())); }
+void* dev_alloc_bytes(size_t bytes);
+void dev_free(void* p);
+template <class T> T* dev_alloc(size_t n) { return static_cast<T*>(dev_alloc_bytes(sizeof(T) * (n ? n : 1))); }
+void copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);        // on cur_stream(), synchronised
 uint32_t next_challenge_seed();        // random_device, or a counter when set_challenge_seed() was called
 }  // namespace zkdl_host
 
 void set_challenge_seed(uint32_t seed);   // 0 restores std::random_device
+void set_thread_challenge_seed(uint32_t seed);   // per-thread seed stream (deterministic proofs from concurrent threads); 0 = use the global one
 
 // ---- constants (g1-tensor.cuh:28-63, bls12-381.cu:3-11)
 extern const Fp_t G1_generator_x_mont, G1_generator_y_mont, G1_ONE;
