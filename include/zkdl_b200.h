@@ -142,6 +142,24 @@ int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const ui
                              const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
                              zkdl_fr_t* proof_fr, void* stream);
 
+/* The same provers restricted to some of their independent parts (sub-layer partition over GPUs).  Only the
+ * selected segments of the proof buffers are written; a rank that owns a part passes the full-size buffers and ships
+ * its segments.  zkFC: ZKDL_FC_SUMCHECK = [ip sumcheck][Z(u)], ZKDL_FC_OPENING = [open ret] + all of proof_g1.
+ * zkReLU: ZKDL_RELU_MAG = [bin(mag)][mag.partial_me], ZKDL_RELU_REM = [bin(rem)][rem.partial_me], ZKDL_RELU_HP = [hadamard]. */
+#define ZKDL_FC_SUMCHECK 1u
+#define ZKDL_FC_OPENING 2u
+#define ZKDL_RELU_MAG 1u
+#define ZKDL_RELU_REM 2u
+#define ZKDL_RELU_HP 4u
+int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
+                          const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
+                          const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
+                          zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, unsigned parts, void* stream);
+int zkdl_zkrelu_prove_packed_parts(const zkdl_fr_t* X, const zkdl_fr_t* sign, const uint32_t* mag_packed, const uint16_t* rem_packed, size_t n,
+                                   const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
+                                   const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
+                                   zkdl_fr_t* proof_fr, unsigned parts, void* stream);
+
 /* ------------------------------------------------------------------ host helpers (proof.cu:3-31) */
 /* random_vec with an injected seed: std::mt19937(seed), 8 draws per element, last % 1944954707 */
 void zkdl_random_vec_host(uint32_t seed, size_t len, zkdl_fr_t* out_host);

@@ -25,7 +25,7 @@ def test_demo_proof_verifies_at_full_size(env):
     zk, mlp, verify, P = env
     proof = P.prove(seed=77)
     assert len(proof) == 15
-    for part, (kind, i, ch) in zip(proof, P.last_tasks):
+    for part, (kind, i, ch, _mask) in zip(proof, P.last_tasks):
         L = P.layers[i]
         if kind == "fc":
             info = verify.verify_zkfc(part[2], part[3], L.G, P.B, L.I, L.O, *ch, gens_table=None)
@@ -38,7 +38,7 @@ def test_demo_proof_verifies_at_full_size(env):
 def test_tampered_proofs_are_rejected(env):
     zk, mlp, verify, P = env
     proof = P.prove(seed=78, fc_layers=[2], relu_layers=[2])
-    (kr, ir, chr_), (kf, if_, chf) = P.last_tasks
+    (kr, ir, chr_, _m1), (kf, if_, chf, _m2) = P.last_tasks
     relu_part = next(p for p in proof if p[0] == "relu"); fc_part = next(p for p in proof if p[0] == "fc")
     L = P.layers[2]
     verify.verify_zkfc(fc_part[2], fc_part[3], L.G, P.B, L.I, L.O, *chf)

@@ -273,3 +273,30 @@ def test_zkrelu_prove(zk, n):
 
 def test_random_vec_matches_oracle(zk):
     assert eq(zk.random_vec(12345, 33), orc.random_vec(12345, 33))
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_subtask_partition_reproduces_the_whole_proof(zk, world):
+    """The sub-layer partition (parallel.partition_subtasks): every rank's pieces, proved separately through the
+    *_parts entry points and re-assembled, are bit-identical to the proof of the undivided prover."""
+    import torch
+    from zkdl_b200 import mlp, parallel
+    dims = [(20, 32), (32, 64), (64, 30), (30, 16)]
+    ws, x = mlp.synthetic_mlp(dims, 8, seed=3)
+    P = mlp.MLPProver(ws, gen_seed=2)
+    P.forward(x)
+    whole = P.prove(seed=11, streams=1)
+    shapes = [(L.I, L.O) for L in P.layers]
+    meta = {(k, i): (L.I, L.ngens, P.B * L.O) for i, L in enumerate(P.layers) for k in ("fc", "relu")}
+    order = [(p[0], p[1]) for p in whole]
+    plans = parallel.partition_subtasks(shapes, P.B, world)
+    flats = []
+    for r in range(world):
+        res = P.prove(seed=11, parts=plans[r], streams=4 if r % 2 else 1)
+        flats.append(parallel.pack_owned(res, plans[r], meta) if res else torch.zeros(0, dtype=torch.int32, device="cuda"))
+    got = parallel.assemble(flats, plans, meta, order)
+    for p in whole:
+        key = (p[0], p[1])
+        assert eq(zk.to_host(got[key][0]), zk.to_host(p[2]))
+        if key[0] == "fc":
+            assert orc.g1_eq(zk.to_host(got[key][1]), zk.to_host(p[3])).all()

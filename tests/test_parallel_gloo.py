@@ -154,3 +154,101 @@ def test_sharded_sumcheck_world2_gloo_matches_single_process():
         p.join(120); assert p.exitcode == 0
     for rank, res in items:
         assert res == {"bin": True, "hp": True, "ip": True}, (rank, res)
+
+
+# ------------------------------------------------------------------------------------------------ sub-layer partition
+DEMO_SHAPES = [(1024, 1024), (1024, 2048)] + [(2048, 2048)] * 5 + [(2048, 1024)]
+
+
+def _demo_meta(B=256):
+    meta, order = {}, []
+    nl = len(DEMO_SHAPES)
+    ngens = [1024, 2048, 2048, 2048, 2048, 2048, 2048, 2048]
+    order.append(("fc", nl - 1))
+    for i in range(nl - 2, -1, -1):
+        order += [("relu", i), ("fc", i)]
+    for i, (I, O) in enumerate(DEMO_SHAPES):
+        meta[("fc", i)] = (I, ngens[i], B * O)
+        meta[("relu", i)] = (I, ngens[i], B * O)
+    return meta, order
+
+
+def test_subtask_partition_covers_every_piece_once_and_balances():
+    for world in (1, 2, 3, 4, 8):
+        plan = parallel.partition_subtasks(DEMO_SHAPES, 256, world)
+        assert plan == parallel.partition_subtasks(DEMO_SHAPES, 256, world)          # deterministic on every rank
+        seen = {}
+        for p in plan:
+            for key, mask in p.items():
+                assert mask and not (seen.get(key, 0) & mask)
+                seen[key] = seen.get(key, 0) | mask
+        assert all(seen[("fc", i)] == 3 for i in range(8)) and all(seen[("relu", i)] == 7 for i in range(7))
+        assert ("relu", 7) not in seen
+        loads = [sum(parallel.subtask_cost(k[0], m, *DEMO_SHAPES[k[1]], 256) for k, mk in p.items() for m in (1, 2, 4) if mk & m)
+                 for p in plan]
+        assert max(loads) <= 1.15 * (sum(loads) / world) + 1e-9
+
+
+def _fake_results(plan_rank, meta, order, full):
+    """What MLPProver.prove(parts=plan_rank) would return: full-size buffers with only the owned rows valid."""
+    res = []
+    for key in order:
+        if key not in plan_rank:
+            continue
+        bufs = [torch.full_like(b, -1) for b in full[key]]
+        for buf, lo, hi in parallel.task_segments(key[0], plan_rank[key], *meta[key]):
+            bufs[buf][lo:hi] = full[key][buf][lo:hi]
+        res.append((key[0], key[1]) + tuple(bufs))
+    return res
+
+
+def _full_proofs(meta, order):
+    g = torch.Generator().manual_seed(5)
+    full = {}
+    for key in order:
+        rows = [0, 0]
+        for buf, lo, hi in parallel.task_segments(key[0], 3 if key[0] == "fc" else 7, *meta[key]):
+            rows[buf] = max(rows[buf], hi)
+        full[key] = [torch.randint(0, 2 ** 31 - 1, (rows[b], (8, 36)[b]), dtype=torch.int32, generator=g)
+                     for b in range(2 if key[0] == "fc" else 1)]
+    return full
+
+
+def test_pack_assemble_roundtrip_local():
+    meta, order = _demo_meta()
+    full = _full_proofs(meta, order)
+    for world in (1, 3, 8):
+        plans = parallel.partition_subtasks(DEMO_SHAPES, 256, world)
+        flats = [parallel.pack_owned(_fake_results(plans[r], meta, order, full), plans[r], meta) for r in range(world)]
+        got = parallel.assemble(flats, plans, meta, order)
+        for key in order:
+            for a, b in zip(got[key], full[key]):
+                assert torch.equal(a, b)
+
+
+def _subtask_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    meta, order = _demo_meta()
+    full = _full_proofs(meta, order)                                   # same seed on every rank
+    plans = parallel.partition_subtasks(DEMO_SHAPES, 256, world)
+    flat = parallel.pack_owned(_fake_results(plans[rank], meta, order, full), plans[rank], meta)
+    got = parallel.gather_proof(flat, world, rank, "cpu")
+    ok = True
+    if rank == 0:
+        asm = parallel.assemble(got, plans, meta, order)
+        ok = all(torch.equal(a, b) for key in order for a, b in zip(asm[key], full[key]))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_subtask_gather_assemble_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_subtask_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    items = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(120); assert p.exitcode == 0
+    assert all(ok for _, ok in items)

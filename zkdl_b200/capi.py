@@ -349,16 +349,47 @@ def open_(gens, com_table, t, u_host):
     return com_eval, proof, ret
 
 
-def zkfc_prove(X, W, Z, B, I, O, gens, com_table, u_bs, u_in, u_out):
+FC_SUMCHECK, FC_OPENING = 1, 2                   # ZKDL_FC_* / ZKDL_RELU_* part masks (include/zkdl_b200.h)
+RELU_MAG, RELU_REM, RELU_HP = 1, 2, 4
+
+
+def zkfc_prove(X, W, Z, B, I, O, gens, com_table, u_bs, u_in, u_out, parts=FC_SUMCHECK | FC_OPENING):
+    """zkFC::prove; `parts` restricts it to the sumcheck and/or the opening (only those proof segments are written)."""
     nfr, ng1 = C.c_size_t(0), C.c_size_t(0)
     lib().zkdl_zkfc_proof_sizes(_sz(B), _sz(I), _sz(O), _sz(gens.n), C.byref(nfr), C.byref(ng1))
     pfr, pg1 = empty(nfr.value, 8), empty(ng1.value, 36)
     k1, p1 = _host_fr(u_bs if len(u_bs) else None)
     k2, p2 = _host_fr(u_in)
     k3, p3 = _host_fr(u_out)
-    _check(lib().zkdl_zkfc_prove(_ptr(X), _ptr(W), _ptr(Z), _sz(B), _sz(I), _sz(O), gens.handle, com_table.handle, p1, p2, p3,
-                                 _ptr(pfr), _ptr(pg1), _stream()))
+    _check(lib().zkdl_zkfc_prove_parts(_ptr(X), _ptr(W), _ptr(Z), _sz(B), _sz(I), _sz(O), gens.handle, com_table.handle, p1, p2, p3,
+                                       _ptr(pfr), _ptr(pg1), C.c_uint(parts), _stream()))
     return pfr, pg1
+
+
+def zkfc_segments(I, parts):
+    """Row ranges of proof_fr written by `parts` (proof_g1 belongs to the opening as a whole)."""
+    nip = 3 * ((I - 1).bit_length()) + 2
+    out = []
+    if parts & FC_SUMCHECK:
+        out.append((0, nip + 1))
+    if parts & FC_OPENING:
+        out.append((nip + 1, nip + 2))
+    return out
+
+
+def zkrelu_segments(n, parts):
+    """Row ranges of the zkReLU proof written by `parts`."""
+    L = (n - 1).bit_length()
+    a = 3 * (L + 5) + 1 + 32
+    b = a + 3 * (L + 4) + 1 + 16
+    out = []
+    if parts & RELU_MAG:
+        out.append((0, a))
+    if parts & RELU_REM:
+        out.append((a, b))
+    if parts & RELU_HP:
+        out.append((b, b + 3 * L + 2))
+    return out
 
 
 def zkrelu_prove(X, sign, mag_bin, rem_bin, u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp):
@@ -369,12 +400,19 @@ def zkrelu_prove(X, sign, mag_bin, rem_bin, u_z, v_z, u_r, v_r, u_rec, u_hp, v_h
     return pfr
 
 
-def zkrelu_prove_packed(X, sign, mag_packed, rem_packed, u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp):
+def zkrelu_prove_packed(X, sign, mag_packed, rem_packed, u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp, parts=RELU_MAG | RELU_REM | RELU_HP):
     n = X.shape[0]
     pfr = empty(lib().zkdl_zkrelu_proof_size(n), 8)
     hs = [_host_fr(a) for a in (u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp)]
-    _check(lib().zkdl_zkrelu_prove_packed(_ptr(X), _ptr(sign), _ptr(mag_packed), _ptr(rem_packed), _sz(n), *[h[1] for h in hs], _ptr(pfr), _stream()))
+    _check(lib().zkdl_zkrelu_prove_packed_parts(_ptr(X), _ptr(sign), _ptr(mag_packed), _ptr(rem_packed), _sz(n), *[h[1] for h in hs],
+                                                _ptr(pfr), C.c_uint(parts), _stream()))
     return pfr
+
+
+def scratch_reserve(nbytes):
+    """Pre-sizes the scratch arenas of the current stream and of the calling thread's side streams (zkdl_scratch_reserve),
+    so that no later call on them has to grow an arena (cudaMalloc + synchronisation) inside a timed region."""
+    _check(lib().zkdl_scratch_reserve(_sz(nbytes), _stream()))
 
 
 def random_vec(seed, n):

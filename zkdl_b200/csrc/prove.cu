@@ -26,8 +26,17 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
                     const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
                     const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
                     zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, void* stream) {
+  return zkdl_zkfc_prove_parts(X, W, Z, B, I, O, gens, com_table, u_bs_host, u_in_host, u_out_host, proof_fr, proof_g1,
+                               ZKDL_FC_SUMCHECK | ZKDL_FC_OPENING, stream);
+}
+
+int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
+                          const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
+                          const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
+                          zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, unsigned parts, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ZK_REQUIRE(X && W && Z && gens && com_table && proof_fr && proof_g1, ZK_ERR_ARG, "null argument");
+  ZK_REQUIRE(parts && !(parts & ~(ZKDL_FC_SUMCHECK | ZKDL_FC_OPENING)), ZK_ERR_ARG, "bad parts mask");
   size_t kb = ilog2(B), ki = ilog2(I), ko = ilog2(O);
   ZK_REQUIRE(((size_t)1 << kb) == B && ((size_t)1 << ki) == I && ((size_t)1 << ko) == O, ZK_ERR_DIM, "Incompatible dimensions 1");
   int rc;
@@ -36,7 +45,7 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
   if ((rc = ss.fork(st))) return rc;
   void* sst = reinterpret_cast<void*>(ss.stream);
   size_t nip = 3 * ki + 2;
-  {
+  if (parts & ZKDL_FC_SUMCHECK) {
     Scratch Xr, Wr;
     if ((rc = Xr.alloc(sizeof(Fr) * I, ss.stream))) return rc;
     if ((rc = Wr.alloc(sizeof(Fr) * I, ss.stream))) return rc;
@@ -52,7 +61,7 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
     if ((rc = zkdl_fr_me(Z, B * O, uz, ko + kb, proof_fr + nip, sst))) return rc;
   }
   // generators.open(weights, com, u_out || u_in)   (zkfc.cu:144)
-  {
+  if (parts & ZKDL_FC_OPENING) {
     zkdl_fr_t uo[64];
     ZK_REQUIRE(ko + ki <= 64, ZK_ERR_DIM, "Incompatible dimensions");
     for (size_t i = 0; i < ko; ++i) uo[i] = u_out_host[i];

@@ -247,16 +247,27 @@ int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const ui
                              const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
                              const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
                              zkdl_fr_t* proof_fr, void* stream) {
+  return zkdl_zkrelu_prove_packed_parts(X, sign, mag_packed, rem_packed, n, u_z_host, v_z_host, u_r_host, v_r_host, u_rec_host,
+                                        u_hp_host, v_hp_host, proof_fr, ZKDL_RELU_MAG | ZKDL_RELU_REM | ZKDL_RELU_HP, stream);
+}
+
+int zkdl_zkrelu_prove_packed_parts(const zkdl_fr_t* X, const zkdl_fr_t* sign, const uint32_t* mag_packed, const uint16_t* rem_packed, size_t n,
+                                   const zkdl_fr_t* u_z_host, const zkdl_fr_t* v_z_host, const zkdl_fr_t* u_r_host, const zkdl_fr_t* v_r_host,
+                                   const zkdl_fr_t* u_rec_host, const zkdl_fr_t* u_hp_host, const zkdl_fr_t* v_hp_host,
+                                   zkdl_fr_t* proof_fr, unsigned parts, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   ZK_REQUIRE(X && sign && mag_packed && rem_packed && proof_fr, ZK_ERR_ARG, "null argument");
+  ZK_REQUIRE(parts && !(parts & ~(ZKDL_RELU_MAG | ZKDL_RELU_REM | ZKDL_RELU_HP)), ZK_ERR_ARG, "bad parts mask");
   size_t L = 0; while (((size_t)1 << L) < n) ++L;
   ZK_REQUIRE(((size_t)1 << L) == n && L >= 1 && L < 27, ZK_ERR_DIM, "Incompatible dimensions");
   int rc;
   Scratch urd, erec;
-  if ((rc = urd.alloc(sizeof(Fr) * L, st))) return rc;
-  ZK_CUDA(cudaMemcpyAsync(urd.p, u_rec_host, sizeof(Fr) * L, cudaMemcpyHostToDevice, st));
-  if ((rc = erec.alloc(sizeof(Fr) * n, st))) return rc;
-  if ((rc = build_eq_table(urd.as<Fr>(), u_rec_host, (int)L, 0, erec.as<Fr>(), st))) return rc;
+  if (parts & (ZKDL_RELU_MAG | ZKDL_RELU_REM)) {
+    if ((rc = urd.alloc(sizeof(Fr) * L, st))) return rc;
+    ZK_CUDA(cudaMemcpyAsync(urd.p, u_rec_host, sizeof(Fr) * L, cudaMemcpyHostToDevice, st));
+    if ((rc = erec.alloc(sizeof(Fr) * n, st))) return rc;
+    if ((rc = build_eq_table(urd.as<Fr>(), u_rec_host, (int)L, 0, erec.as<Fr>(), st))) return rc;
+  }
   Fr* p = reinterpret_cast<Fr*>(proof_fr);
   Fr* p_mag_sc = p;                       p += 3 * (L + 5) + 1;
   Fr* p_mag_rec = p;                      p += 32;
@@ -266,9 +277,12 @@ int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const ui
   SideStream& s1 = side_stream(1); SideStream& s2 = side_stream(2);
   if ((rc = s1.fork(st))) return rc;
   if ((rc = s2.fork(st))) return rc;
-  if ((rc = packed_bin_and_recover<32, uint32_t>(mag_packed, n, L, u_z_host, v_z_host, erec.as<Fr>(), p_mag_sc, p_mag_rec, st))) return rc;
-  if ((rc = packed_bin_and_recover<16, uint16_t>(rem_packed, n, L, u_r_host, v_r_host, erec.as<Fr>(), p_rem_sc, p_rem_rec, s1.stream))) return rc;
-  if ((rc = zkdl_hp_sumcheck(X, sign, n, u_hp_host, v_hp_host, L, reinterpret_cast<zkdl_fr_t*>(p), reinterpret_cast<void*>(s2.stream)))) return rc;   // zkrelu.cu:99
+  if ((parts & ZKDL_RELU_MAG) &&
+      (rc = packed_bin_and_recover<32, uint32_t>(mag_packed, n, L, u_z_host, v_z_host, erec.as<Fr>(), p_mag_sc, p_mag_rec, st))) return rc;
+  if ((parts & ZKDL_RELU_REM) &&
+      (rc = packed_bin_and_recover<16, uint16_t>(rem_packed, n, L, u_r_host, v_r_host, erec.as<Fr>(), p_rem_sc, p_rem_rec, s1.stream))) return rc;
+  if ((parts & ZKDL_RELU_HP) &&
+      (rc = zkdl_hp_sumcheck(X, sign, n, u_hp_host, v_hp_host, L, reinterpret_cast<zkdl_fr_t*>(p), reinterpret_cast<void*>(s2.stream)))) return rc;   // zkrelu.cu:99
   if ((rc = s1.join(st))) return rc;
   return s2.join(st);
 }

@@ -69,10 +69,12 @@ class MLPProver:
                 cur = a
         return self.Z[-1]
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None):
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None, parts=None):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
-        fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); challenges are drawn for
-        every layer regardless, so a layer's proof does not depend on which rank produced it.
+        fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); `parts` = {("fc"|"relu", layer):
+        part mask} restricts it further to independent parts of a layer's proof (parallel.partition_subtasks): the
+        returned buffers are full-size with only the owned segments written.  Challenges are drawn for every layer
+        regardless, so a proof element does not depend on which rank produced it.
         Every layer's proof is independent of the others (all randomness is fresh), so the per-layer
         proofs are issued on `streams` CUDA streams: the latency-bound bucket reductions of one layer's opening overlap
         the bandwidth-bound sumcheck passes of another.  With threads=True each stream is fed by its own host thread
@@ -92,44 +94,71 @@ class MLPProver:
         nl = len(self.layers)
         tasks = []                                   # (kind, layer, challenges) in the reference's order
 
+        def owned(kind, i, every):
+            if parts is not None:
+                return parts.get((kind, i), 0)
+            sel = fc_layers if kind == "fc" else relu_layers
+            return every if sel is None or i in sel else 0
+
         def fc(i):
             L = self.layers[i]
+            mask = owned("fc", i, zk.FC_SUMCHECK | zk.FC_OPENING)
+            if not mask:
+                ctr[0] += 3                                                                  # another rank draws these
+                return
             ch = (rv(kb), rv(ceil_log2(L.I)), rv(ceil_log2(L.O)))                             # zkfc.cu:135-137
-            if fc_layers is None or i in fc_layers:
-                tasks.append(("fc", i, ch))
+            tasks.append(("fc", i, ch, mask))
 
         def relu(i):
+            mask = owned("relu", i, zk.RELU_MAG | zk.RELU_REM | zk.RELU_HP)
+            if not mask:
+                ctr[0] += 7
+                return
             Lg = ceil_log2(B * self.layers[i].O)
             ch = [rv(Lg + 5), rv(Lg + 5), rv(Lg + 4), rv(Lg + 4), rv(Lg)]                    # zkrelu.cu:85-89
             ch += [rv(Lg), rv(Lg)]                                                           # zkrelu.cu:97-98
-            if relu_layers is None or i in relu_layers:
-                tasks.append(("relu", i, ch))
+            tasks.append(("relu", i, ch, mask))
 
         fc(nl - 1)
         for i in range(nl - 2, -1, -1):
             relu(i)
             fc(i)
 
-        self.last_tasks = tasks                       # (kind, layer, challenges): what a verifier needs besides the proof
+        self.last_tasks = tasks                       # (kind, layer, challenges, parts): what a verifier needs besides the proof
 
         def run(task):
-            kind, i, ch = task
+            kind, i, ch, mask = task
             L = self.layers[i]
             if kind == "fc":
                 Xin = self.A[i - 1] if i > 0 else self.X
-                return ("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, *ch)
+                return ("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, *ch, parts=mask)
             sign, mag, rem = self.aux[i]
-            return ("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch))
+            return ("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch, parts=mask))
 
         main = torch.cuda.current_stream()
         if streams <= 1 or len(tasks) <= 1:
             return [run(t) for t in tasks]
-        if len(getattr(self, "_streams", [])) != streams:
-            self._streams = [torch.cuda.Stream() for _ in range(streams)]
-            from concurrent.futures import ThreadPoolExecutor
-            self._pool = ThreadPoolExecutor(max_workers=streams)
-        start = torch.cuda.Event(); start.record(main)
+        streams = min(streams, len(tasks))
         dev = torch.cuda.current_device()
+        if len(getattr(self, "_streams", [])) < streams:
+            # One CUDA stream and ONE dedicated host thread per slot: the library's side streams and scratch arenas are
+            # per host thread / per stream, so a stable slot <-> thread pairing keeps every arena at its final size after
+            # the first call (a shared pool that shuffles slots over threads grows arenas sporadically for many calls).
+            from concurrent.futures import ThreadPoolExecutor
+            old = len(getattr(self, "_streams", []))
+            self._streams = getattr(self, "_streams", []) + [torch.cuda.Stream() for _ in range(streams - old)]
+            self._pools = getattr(self, "_pools", []) + [ThreadPoolExecutor(max_workers=1) for _ in range(streams - old)]
+            need = 256 * max(max(L.I * L.O, 4 * B * L.O) for L in self.layers)
+
+            def reserve(slot):
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(self._streams[slot]):
+                    zk.scratch_reserve(need)
+
+            for f in [self._pools[s_].submit(reserve, s_) for s_ in range(old, streams)]:
+                f.result()
+            torch.cuda.synchronize()
+        start = torch.cuda.Event(); start.record(main)
 
         def worker(slot):
             torch.cuda.set_device(dev)
@@ -143,7 +172,7 @@ class MLPProver:
             return res, ev
 
         if threads:
-            outs = list(self._pool.map(worker, range(streams)))
+            outs = [f.result() for f in [self._pools[s_].submit(worker, s_) for s_ in range(streams)]]
         else:
             outs = [worker(s_) for s_ in range(streams)]
         out = [None] * len(tasks)

@@ -14,6 +14,104 @@ def partition_layers(n_layers, world, rank):
     return fc, relu
 
 
+# ------------------------------------------------------------------------------------------------ sub-layer partition
+# A layer's proof is itself several independent pieces (include/zkdl_b200.h, ZKDL_FC_* / ZKDL_RELU_*): zkFC = the matmul
+# sumcheck + the commitment opening; zkReLU = the binary sumcheck of mag_bin, the one of rem_bin, the Hadamard sumcheck.
+# Partitioning these 37 pieces of the demo MLP (instead of 15 whole layers) lets 8 ranks balance to within a piece.
+FC_MASKS = (1, 2)
+RELU_MASKS = (1, 2, 4)
+
+
+def _clog2(n):
+    return 0 if n <= 1 else (int(n) - 1).bit_length()
+
+
+def subtask_cost(kind, mask, I, O, B):
+    """Latency (ms) of one piece run alone on an idle B200, fitted to tools/probe_subtasks.py on the demo shapes."""
+    if kind == "fc":
+        return 0.49 if mask == 1 else 1.2 + 0.06 * (I * O / 2 ** 20)
+    n = B * O / 2 ** 20
+    return {1: 0.5 + 0.92 * n, 2: 0.42 + 0.66 * n, 4: 0.5}[mask]
+
+
+def partition_subtasks(shapes, B, world, costs=None):
+    """shapes: [(I, O)] padded layer shapes.  Returns one dict per rank {("fc"|"relu", layer): part mask}.
+    Longest-processing-time greedy over the pieces; among equally loaded ranks a piece joins the rank that already owns
+    another piece of the same layer proof (they share a table).  Deterministic: every rank computes the same plan."""
+    pieces = []
+    for i, (I, O) in enumerate(shapes):
+        for m in FC_MASKS:
+            pieces.append((("fc", i), m, I, O))
+        if i + 1 < len(shapes):
+            for m in RELU_MASKS:
+                pieces.append((("relu", i), m, I, O))
+    cost = lambda pc: (costs or {}).get((pc[0], pc[1]), subtask_cost(pc[0][0], pc[1], pc[2], pc[3], B))
+    pieces.sort(key=lambda pc: (-cost(pc), pc[0][1], pc[0][0], pc[1]))
+    load = [0.0] * world
+    plan = [dict() for _ in range(world)]
+    for pc in pieces:
+        r = min(range(world), key=lambda q: (round(load[q], 6), 0 if pc[0] in plan[q] else 1, q))
+        plan[r][pc[0]] = plan[r].get(pc[0], 0) | pc[1]
+        load[r] += cost(pc)
+    return plan
+
+
+def task_segments(kind, mask, I, ngens, n):
+    """[(buf, lo, hi)]: rows of the proof buffers a part mask writes.  buf 0 = Fr rows (8 limbs), buf 1 = G1 rows (36)."""
+    segs = []
+    if kind == "fc":
+        nip = 3 * _clog2(I) + 2
+        if mask & 1:
+            segs.append((0, 0, nip + 1))
+        if mask & 2:
+            segs += [(0, nip + 1, nip + 2), (1, 0, 3 * _clog2(ngens) + 2)]
+        return segs
+    L = _clog2(n)
+    a = 3 * (L + 5) + 1 + 32
+    b = a + 3 * (L + 4) + 1 + 16
+    for bit, lo, hi in ((1, 0, a), (2, a, b), (4, b, b + 3 * L + 2)):
+        if mask & bit:
+            segs.append((0, lo, hi))
+    return segs
+
+
+def pack_owned(results, plan_rank, meta):
+    """results: [(kind, layer, proof_fr[, proof_g1])] as MLPProver.prove(parts=plan_rank) returns them (full-size
+    buffers, only the owned segments written).  Returns the owned segments as one flat tensor.
+    meta[(kind, layer)] = (I, ngens, n)."""
+    out = []
+    for res in results:
+        key = (res[0], res[1])
+        for buf, lo, hi in task_segments(key[0], plan_rank[key], *meta[key]):
+            out.append(res[2 + buf][lo:hi].reshape(-1))
+    return torch.cat(out)
+
+
+def assemble(flats, plans, meta, order):
+    """Inverse of pack_owned over all ranks: flats[r] = rank r's flat tensor, plans = partition_subtasks(...),
+    order = [(kind, layer)] in proving order.  Returns {(kind, layer): [proof_fr] or [proof_fr, proof_g1]}."""
+    width = (8, 36)
+    full = {}
+    for key in order:
+        I, ngens, n = meta[key]
+        every = 3 if key[0] == "fc" else 7
+        rows = [0, 0]
+        for buf, lo, hi in task_segments(key[0], every, I, ngens, n):
+            rows[buf] = max(rows[buf], hi)
+        full[key] = [flats[0].new_zeros((rows[b], width[b])) for b in range(2 if key[0] == "fc" else 1)]
+    for r, plan in enumerate(plans):
+        off = 0
+        for key in order:
+            if key not in plan:
+                continue
+            for buf, lo, hi in task_segments(key[0], plan[key], *meta[key]):
+                cnt = (hi - lo) * width[buf]
+                full[key][buf][lo:hi] = flats[r][off: off + cnt].reshape(hi - lo, width[buf])
+                off += cnt
+        assert off == flats[r].numel(), "flat proof of rank %d does not match its plan" % r
+    return full
+
+
 def gather_proof(flat, world, rank, device, sizes=None):
     """Gathers each rank's flat proof tensor on rank 0.  Returns the list of per-rank tensors on rank 0, None elsewhere.
     `sizes` (elements per rank) is known in advance for a given model shape: passing it avoids the size exchange and
