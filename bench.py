@@ -378,7 +378,7 @@ def main():
     extra["commit_msm_mpts_s"] = (L2.I * L2.O) / (extra["commit_2048x2048_ms"] * 1e-3) / 1e6
     extra["setup_s"] = setup_s
 
-    cpu = None if args.skip_cpu_baseline else cpu_baseline_sample()
+    cpu = None if (args.skip_cpu_baseline or world > 1) else cpu_baseline_sample()      # host baseline: rank 0 at N=1 only
     line = {"metric": METRIC, "value": ms / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs (Fr 255-bit / Fq 381-bit modular)", "data": "synthetic",
