@@ -350,24 +350,44 @@ __global__ void __launch_bounds__(G1_THREADS) k_msm_combine_heavy(const G1XYZZ* 
   if (lane == 0) buckets[key] = tmp;
 }
 
-// `split` CTAs per window group: CTA j reduces buckets [j*K/split, (j+1)*K/split) to sum_k k * B_k (global bucket
-// numbers) with per-thread running sums + a small-scalar offset + a shared-memory tree; k_msm_final adds the pieces.
+// `split` CTAs per window group: CTA j reduces buckets [j*K/split, (j+1)*K/split) to sum_b (b + 1) * B_b (global bucket
+// numbers); k_msm_final adds the pieces.  Thread t owns L consecutive buckets: run_t = their sum, tot_t = their sum
+// with local weights 1..L (running sums, 2L additions).  The thread offsets then need sum_t t * run_t, which is the
+// sum over s >= 1 of the suffix sums E_s = sum_{t >= s} run_t: one Hillis-Steele suffix scan (log T additions per
+// thread) replaces a 12-bit double-and-add per thread, which had been 2/3 of this kernel's field multiplications.
 __global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, int split, G1XYZZ* __restrict__ group_out) {
   G1XYZZ* sm = reinterpret_cast<G1XYZZ*>(g1_dyn_smem);
   const int group = blockIdx.x / split, piece = blockIdx.x % split;
   const int Kp = K / split;                                   // buckets in this piece
   const G1XYZZ* B = buckets + (size_t)group * K;
-  int T = blockDim.x;
-  int L = Kp >= T ? Kp / T : 1;                               // K, split and T are powers of two
-  int lo = piece * Kp + threadIdx.x * L;
-  G1XYZZ val = xyzz_inf();
-  if (threadIdx.x * L < Kp) {
-    G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
+  const int T = blockDim.x, t = threadIdx.x;
+  const int L = Kp >= T ? Kp / T : 1;                         // K, split and T are powers of two
+  const int Tp = Kp / L;                                      // threads that own buckets (<= T)
+  G1XYZZ run = xyzz_inf(), tot = xyzz_inf();
+  if (t < Tp) {
+    const int lo = piece * Kp + t * L;
     for (int b = lo + L - 1; b >= lo; --b) { run = xyzz_add(run, B[b]); tot = xyzz_add(tot, run); }
-    val = lo ? xyzz_add(tot, xyzz_mul_small(run, (uint32_t)lo)) : tot;
+  }
+  G1XYZZ E = run;                                             // -> inclusive suffix sum of run over the threads
+  sm[t] = E;
+  __syncthreads();
+  for (int d = 1; d < Tp; d <<= 1) {
+    const bool act = t + d < Tp;
+    G1XYZZ o;
+    if (act) o = sm[t + d];
+    __syncthreads();
+    if (act) { E = xyzz_add(E, o); sm[t] = E; }
+    __syncthreads();
+  }
+  G1XYZZ val = tot;
+  if (t > 0 && t < Tp) {
+    for (int l = L; l > 1; l >>= 1) E = xyzz_dbl(E);          // L * E_t
+    val = xyzz_add(tot, E);
+  } else if (t == 0 && piece) {
+    val = xyzz_add(tot, xyzz_mul_small(E, (uint32_t)(piece * Kp)));   // this piece's offset times its total
   }
   G1XYZZ r = block_sum_xyzz(val, sm);
-  if (threadIdx.x == 0) group_out[blockIdx.x] = r;
+  if (t == 0) group_out[blockIdx.x] = r;
 }
 __global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int split, int c, G1Jac* __restrict__ out) {
   size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -519,9 +539,11 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   uint32_t* hcount = heavy.as<uint32_t>(); uint32_t* hlist = hcount + 1;
   ZK_LAUNCH(k_msm_combine<<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
   ZK_LAUNCH(k_msm_combine_heavy<<<div_up(max_heavy * 32, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), buckets.as<G1XYZZ>(), hlist, hcount));
-  // reduce: 256-thread CTAs, at most 2 buckets per thread
-  int T = cfg.K < 32 ? 32 : (cfg.K > 256 ? 256 : cfg.K);
-  int split = cfg.K / (T * 2); if (split < 1) split = 1; if (split > 16) split = 16;
+  // reduce: up to 256-thread CTAs, RL (8) buckets per thread, more only when 16 CTAs per group are not enough
+  static const int RL = getenv("ZKDL_MSM_RED_L") ? atoi(getenv("ZKDL_MSM_RED_L")) : 8;      // tuning knobs (powers of two)
+  static const int RT = getenv("ZKDL_MSM_RED_T") ? atoi(getenv("ZKDL_MSM_RED_T")) : 256;
+  int T = cfg.K / RL; if (T < 32) T = 32; if (T > RT) T = RT; if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;
+  int split = cfg.K / (T * RL); if (split < 1) split = 1; if (split > 16) split = 16;
   if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG * split, st))) return rc;
   ZK_LAUNCH(k_msm_reduce<<<(unsigned)(m * cfg.NG * split), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, split, groups.as<G1XYZZ>()));
   ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, split, cfg.c, out));
