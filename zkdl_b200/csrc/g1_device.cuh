@@ -25,13 +25,14 @@ ZK_HD uint32_t get_bits(const Fr& a, int pos, int c) {
   if (off + c > 32 && limb + 1 < 8) lo |= a.v[limb + 1] << (32 - off);
   return lo & ((1u << c) - 1u);
 }
-// signed digit of window w (width c): value in [-2^(c-1)+1, 2^(c-1)], carry threaded by the caller
-ZK_HD int32_t next_digit(const Fr& mag, int w, int c, uint32_t& carry) {
-  uint32_t raw = get_bits(mag, w * c, c) + carry;
+// signed digit of the c-bit window starting at bit pos: value in [-2^(c-1)+1, 2^(c-1)], carry threaded by the caller
+ZK_HD int32_t next_digit_at(const Fr& mag, int pos, int c, uint32_t& carry) {
+  uint32_t raw = get_bits(mag, pos, c) + carry;
   if (raw > (1u << (c - 1))) { carry = 1; return (int32_t)raw - (int32_t)(1u << c); }
   carry = 0;
   return (int32_t)raw;
 }
+ZK_HD int32_t next_digit(const Fr& mag, int w, int c, uint32_t& carry) { return next_digit_at(mag, w * c, c, carry); }
 
 // a^(p-2) in Fq (the reference has no inversion; used for table normalisation and zkdl_g1_normalize)
 ZK_HD Fq fq_inv(const Fq& a) {

@@ -165,6 +165,9 @@ struct MsmCfg {
   int NG;               // window groups per row: 1 with full tables, W otherwise
   int full, tstep;      // full tables; table windows per digit window (c / TABLE_C)
   int mont;             // scalars are Montgomery
+  int nfull, ctop;      // windows [0, nfull) are c bits wide, the remaining top ones ctop bits (full tables only: every
+                        // window feeds the same bucket set, so narrow top windows keep the 255-bit scalar's last few
+                        // bits from piling 1/W of all entries into three buckets)
 };
 
 template <bool SCATTER>
@@ -177,7 +180,8 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
     if (mag.is_zero()) continue;
     uint32_t carry = 0;
     for (int w = 0; w < cfg.W; ++w) {
-      int32_t d = next_digit(mag, w, cfg.c, carry);
+      const int bit = w < cfg.nfull ? w * cfg.c : cfg.nfull * cfg.c + (w - cfg.nfull) * cfg.ctop;
+      int32_t d = next_digit_at(mag, bit, w < cfg.nfull ? cfg.c : cfg.ctop, carry);
       if (d == 0) continue;
       uint32_t ad = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
       size_t key = (row * cfg.NG + (cfg.full ? 0 : w)) * (size_t)cfg.K + (ad - 1);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(256) k_msm_digits(const Fr* __restrict__ scala
         atomicAdd(&counters[key], 1u);
       } else {
         uint32_t pos = atomicAdd(&counters[key], 1u);
-        uint32_t base = cfg.full ? (uint32_t)((size_t)w * cfg.tstep * cfg.n + i) : (uint32_t)i;
+        uint32_t base = cfg.full ? (uint32_t)((size_t)(bit / TABLE_C) * cfg.n + i) : (uint32_t)i;
         entries[pos] = base | ((negative != (d < 0)) ? 0x80000000u : 0u);
       }
     }
@@ -494,6 +498,8 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   if (cfg.full) { cfg.c = (cfg.c / TABLE_C) * TABLE_C; if (cfg.c < TABLE_C) cfg.c = TABLE_C; if (cfg.c > 16) cfg.c = 16; }
   cfg.tstep = cfg.c / TABLE_C;
   cfg.W = cfg.full ? (255 + cfg.c - 1) / cfg.c : (maxbits + 1 + cfg.c - 1) / cfg.c;
+  cfg.nfull = cfg.W; cfg.ctop = cfg.c;
+  if (cfg.full && cfg.c == 12) { cfg.nfull = 20; cfg.ctop = 8; cfg.W = 22; }      // 20 x 12 + 2 x 8 = 256 bits: 7 bits reach the top window
   cfg.K = 1 << (cfg.c - 1);
   cfg.NG = cfg.full ? 1 : cfg.W;
   size_t nkeys = m * (size_t)cfg.NG * cfg.K;
