@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __res
 // integer dot product (128-bit accumulator) reduced mod p is the same field element as the Fr dot product, so the result
 // is bit-identical; ~5 integer instructions per multiply-add instead of a 136-IMAD Montgomery product.  Any operand
 // outside the range raises `flag`, and the generic Fr kernel (launched right after, exiting early otherwise) recomputes.
-__global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in, int32_t* __restrict__ out, size_t n, uint32_t* __restrict__ flag) {
+// flag[0] |= 1 if an element is not a 32-bit signed integer; *maxmag = max |element| (decides the accumulator width)
+__global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in, int32_t* __restrict__ out, size_t n, uint32_t* __restrict__ flag,
+                                                       uint32_t* __restrict__ maxmag) {
+  uint32_t mymax = 0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     Fr x = from_mont(in[i]);
     bool hi0 = (x.v[1] | x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7]) == 0;
@@ -305,16 +308,22 @@ __global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in
       else atomicOr(flag, 1u);
     }
     out[i] = r;
+    uint32_t mag = r < 0 ? 0u - (uint32_t)r : (uint32_t)r;
+    if (mag > mymax) mymax = mag;
   }
+  mymax = __reduce_max_sync(0xffffffffu, mymax);
+  if ((threadIdx.x & 31) == 0 && mymax) atomicMax(maxmag, mymax);
 }
 static constexpr int IM_T = 64, IM_K = 32;                    // 64x64 outputs per CTA, 4x4 per thread, K tiles of 32
-__global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
-                                                    size_t rowsA, size_t colsA, size_t colsB) {
-  __shared__ __align__(16) int32_t As[IM_K][IM_T + 4];        // [k][row], padded: 16-byte aligned rows, 4-way store conflicts at most
-  __shared__ __align__(16) int32_t Ws[IM_K][IM_T];            // [k][col]
+// Exact integer product tile.  ACC = int64_t when max|A| * max|W| * colsA < 2^62 (the quantised demo: 2^19 * 2^12 * 2^11),
+// else __int128 (always exact for 32-bit operands).
+template <typename ACC>
+__device__ __forceinline__ void i32_matmul_tile(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
+                                                size_t rowsA, size_t colsA, size_t colsB,
+                                                int32_t (*As)[IM_T + 4], int32_t (*Ws)[IM_T]) {
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const size_t row0 = (size_t)blockIdx.y * IM_T, col0 = (size_t)blockIdx.x * IM_T;
-  __int128 acc[4][4];
+  ACC acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ 
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += (__int128)((int64_t)a[i] * (int64_t)w[j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] += (ACC)((int64_t)a[i] * (int64_t)w[j]);
     }
     __syncthreads();
   }
@@ -355,6 +364,16 @@ __global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ 
       r = to_mont(r);
       C[gr * colsB + gc] = negative ? neg(r) : r;
     }
+}
+// info[0] = not-all-small flag, info[1] = max|A|, info[2] = max|W|, info[3] = force the 128-bit accumulator (tuning knob)
+__global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
+                                                    size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ info) {
+  __shared__ __align__(16) int32_t As[IM_K][IM_T + 4];        // [k][row], padded: 16-byte aligned rows, 4-way store conflicts at most
+  __shared__ __align__(16) int32_t Ws[IM_K][IM_T];            // [k][col]
+  if (info[0]) return;                                         // the generic Fr kernel takes over
+  const unsigned long long bound = (unsigned long long)info[1] * (unsigned long long)info[2];
+  if (!info[3] && bound <= (1ull << 62) / (colsA ? colsA : 1)) i32_matmul_tile<long long>(A, W, C, rowsA, colsA, colsB, As, Ws);
+  else i32_matmul_tile<__int128>(A, W, C, rowsA, colsA, colsB, As, Ws);
 }
 
 // relu: Z, sign and the packed decomposition (q: u32 rescaled magnitude, r: u16 = rem_mag | rem_sign << 15)
@@ -616,12 +635,14 @@ int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t 
   Scratch ai, wi, flag; int rc;
   if ((rc = ai.alloc(sizeof(int32_t) * rowsA * colsA, st))) return rc;
   if ((rc = wi.alloc(sizeof(int32_t) * colsA * colsB, st))) return rc;
-  if ((rc = flag.alloc(sizeof(uint32_t), st))) return rc;
-  ZK_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), st));
-  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(F(A), ai.as<int32_t>(), rowsA * colsA, flag.as<uint32_t>()));
-  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(colsA * colsB, THREADS), THREADS, 0, st>>>(F(B), wi.as<int32_t>(), colsA * colsB, flag.as<uint32_t>()));
+  if ((rc = flag.alloc(sizeof(uint32_t) * 4, st))) return rc;
+  static const uint32_t force128 = getenv("ZKDL_MM_FORCE128") ? 1u : 0u;                     // tuning knob
+  ZK_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * 4, st));
+  if (force128) ZK_CUDA(cudaMemsetAsync(flag.as<uint32_t>() + 3, 1, 1, st));
+  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(F(A), ai.as<int32_t>(), rowsA * colsA, flag.as<uint32_t>(), flag.as<uint32_t>() + 1));
+  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(colsA * colsB, THREADS), THREADS, 0, st>>>(F(B), wi.as<int32_t>(), colsA * colsB, flag.as<uint32_t>(), flag.as<uint32_t>() + 2));
   dim3 igrid(div_up(colsB, IM_T), div_up(rowsA, IM_T));
-  ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), wi.as<int32_t>(), F(C), rowsA, colsA, colsB));
+  ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), wi.as<int32_t>(), F(C), rowsA, colsA, colsB, flag.as<uint32_t>()));
   dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
   ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, st>>>(F(A), F(B), F(C), rowsA, colsA, colsB, flag.as<uint32_t>()));
   return ZK_OK;
