@@ -69,6 +69,13 @@ int zkdl_bin_sumcheck(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, con
 int zkdl_float_to_fr(const float* fs, zkdl_fr_t* out, uint32_t rows_in, uint32_t rows_out, uint32_t cols_in, uint32_t cols_out, void* stream);
 /* matrixMultiplyOptimized (zkfc.cu:6-47): C[rowsA x colsB] = A[rowsA x colsA] * B[colsA x colsB] over Fr (Montgomery) */
 int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t rowsA, size_t colsA, size_t colsB, void* stream);
+/* A zkFC multiplies by the same weight matrix on every call (zkfc.cu:117-126): zkdl_mm_weights keeps its quantised
+ * integer copy (int32 + byte planes for the int8 tensor cores) so that zkdl_fr_matmul_prepared does not re-derive it.
+ * Results are identical to zkdl_fr_matmul's; W must be the table the copy was made from and must not change meanwhile. */
+typedef struct zkdl_mm_weights zkdl_mm_weights;
+int zkdl_mm_weights_create(const zkdl_fr_t* W, size_t rows, size_t cols, zkdl_mm_weights** out, void* stream);
+int zkdl_mm_weights_destroy(zkdl_mm_weights* w);
+int zkdl_fr_matmul_prepared(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_mm_weights* prep, zkdl_fr_t* C, size_t rowsA, void* stream);
 /* relu_kernel (zkrelu.cu:11-41): Z[n], sign[n], mag_bin[32n], rem_bin[16n].  Inputs outside +-2^47 (undefined in the
  * reference) give sign = 0, mag = 0 and are counted in *out_of_range (device u32, may be NULL). */
 int zkdl_relu(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, uint32_t* out_of_range, void* stream);

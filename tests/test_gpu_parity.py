@@ -129,6 +129,38 @@ def test_quantise_matmul_relu(zk):
     assert eq(zk.to_host(Z), oZ) and eq(zk.to_host(sign), osign) and eq(zk.to_host(mag), omag) and eq(zk.to_host(rem), orem)
 
 
+@pytest.mark.parametrize("case", ["tc_small", "tc_boundary", "a_too_big", "w_too_big", "generic_fr", "ragged_shape", "tc_long_k"])
+def test_matmul_prepared_routes(zk, case):
+    """zkdl_fr_matmul_prepared: the int8 tensor-core route, the int32 SIMT route and the generic Fr route agree with the
+    oracle's Fr matmul bit for bit; the route is picked on the device from the operands' magnitudes."""
+    M, K, N = 64, 128, 64
+    if case == "ragged_shape":
+        M, K, N = 24, 40, 33
+    if case == "tc_long_k":
+        M, K, N = 128, 2048, 128
+    amax, wmax = (1 << 23) - 1, (1 << 15) - 1
+    if case in ("tc_small", "ragged_shape", "tc_long_k"):
+        a = [int(v) for v in rng.integers(-(1 << 20), 1 << 20, size=M * K)]
+        w = [int(v) for v in rng.integers(-(1 << 12), 1 << 12, size=K * N)]
+    elif case == "generic_fr":
+        a = w = None
+    else:
+        a = [(amax, -amax, 0, 1, -1, 255, -256, 65535, -65536)[i % 9] for i in range(M * K)]
+        w = [(wmax, -wmax, 0, 1, -1, 255, -256, 128, -129)[(5 * i + 2) % 9] for i in range(K * N)]
+        if case == "a_too_big":
+            a[7] = 1 << 23
+        if case == "w_too_big":
+            w[11] = -(1 << 15)
+    A = rand_fr(M * K) if a is None else orc.fr_from_ints(a, mont=True)
+    W = rand_fr(K * N) if w is None else orc.fr_from_ints(w, mont=True)
+    dW = zk.to_device(W)
+    prep = zk.MatmulWeights(dW, K, N)
+    got = zk.to_host(zk.fr_matmul_prepared(zk.to_device(A), prep, M))
+    assert eq(got, orc.fr_matmul(A, W, M, K, N))
+    assert eq(zk.to_host(zk.fr_matmul(zk.to_device(A), dW, M, K, N)), got)
+    prep.close()
+
+
 def make_points(n, seed=5):
     r = np.random.default_rng(seed)
     ks = orc.to_limbs([int.from_bytes(r.bytes(31), "little") for _ in range(n)])

@@ -222,6 +222,36 @@ def fr_matmul(A, B, rows_a, cols_a, cols_b):
     return out
 
 
+class MatmulWeights:
+    """Quantised integer copy of a weight table for fr_matmul (zkdl_mm_weights)."""
+
+    def __init__(self, W, rows, cols):
+        if W.shape[0] != rows * cols:
+            raise DimensionError(1, "Incompatible dimensions")
+        self.W, self.rows, self.cols = W, rows, cols
+        self.handle = C.c_void_p()
+        _check(lib().zkdl_mm_weights_create(_ptr(W), _sz(rows), _sz(cols), C.byref(self.handle), _stream()))
+
+    def close(self):
+        if self.handle:
+            lib().zkdl_mm_weights_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def fr_matmul_prepared(A, weights, rows_a):
+    if A.shape[0] != rows_a * weights.rows:
+        raise DimensionError(1, "Incompatible dimensions")
+    out = empty(rows_a * weights.cols, 8)
+    _check(lib().zkdl_fr_matmul_prepared(_ptr(A), _ptr(weights.W), weights.handle, _ptr(out), _sz(rows_a), _stream()))
+    return out
+
+
 def relu(X):
     torch = _torch()
     n = X.shape[0]

@@ -266,116 +266,6 @@ __global__ void __launch_bounds__(THREADS) k_float_to_fr(const float* __restrict
   }
 }
 
-static constexpr int MM_TILE = 16;
-// C = A * B over Fr; 16x16 output tile per CTA, K-tiles staged through shared memory.
-__global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
-                                                                 size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ only_if) {
-  if (only_if && *only_if == 0) return;                      // the small-integer fast path already produced C
-  __shared__ Fr As[MM_TILE][MM_TILE];
-  __shared__ Fr Bs[MM_TILE][MM_TILE];
-  const int tx = threadIdx.x % MM_TILE, ty = threadIdx.x / MM_TILE;
-  const size_t row = (size_t)blockIdx.y * MM_TILE + ty, col = (size_t)blockIdx.x * MM_TILE + tx;
-  Fr sum = Fr::zero();
-  for (size_t k0 = 0; k0 < colsA; k0 += MM_TILE) {
-    As[ty][tx] = (row < rowsA && k0 + tx < colsA) ? A[row * colsA + k0 + tx] : Fr::zero();
-    Bs[ty][tx] = (k0 + ty < colsA && col < colsB) ? B[(k0 + ty) * colsB + col] : Fr::zero();
-    __syncthreads();
-#pragma unroll 4
-    for (int k = 0; k < MM_TILE; ++k) sum = add(sum, mul(As[ty][k], Bs[k][tx]));
-    __syncthreads();
-  }
-  if (row < rowsA && col < colsB) C[row * colsB + col] = sum;
-}
-
-// ---- small-integer fast path of the forward matmul.  Quantised activations and weights are Montgomery forms of small
-// signed integers (|v| < 2^31: inputs at scale 2^16, rescaled activations are u32 magnitudes, zkrelu.cu:29).  The exact
-// integer dot product (128-bit accumulator) reduced mod p is the same field element as the Fr dot product, so the result
-// is bit-identical; ~5 integer instructions per multiply-add instead of a 136-IMAD Montgomery product.  Any operand
-// outside the range raises `flag`, and the generic Fr kernel (launched right after, exiting early otherwise) recomputes.
-// flag[0] |= 1 if an element is not a 32-bit signed integer; *maxmag = max |element| (decides the accumulator width)
-__global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in, int32_t* __restrict__ out, size_t n, uint32_t* __restrict__ flag,
-                                                       uint32_t* __restrict__ maxmag) {
-  uint32_t mymax = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    Fr x = from_mont(in[i]);
-    bool hi0 = (x.v[1] | x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7]) == 0;
-    int32_t r = 0;
-    if (hi0 && x.v[0] < 0x80000000u) r = (int32_t)x.v[0];
-    else {
-      Fr m = sub(Fr::zero(), x);                              // p - x
-      bool mhi0 = (m.v[1] | m.v[2] | m.v[3] | m.v[4] | m.v[5] | m.v[6] | m.v[7]) == 0;
-      if (mhi0 && m.v[0] <= 0x80000000u) r = (int32_t)(0u - m.v[0]);
-      else atomicOr(flag, 1u);
-    }
-    out[i] = r;
-    uint32_t mag = r < 0 ? 0u - (uint32_t)r : (uint32_t)r;
-    if (mag > mymax) mymax = mag;
-  }
-  mymax = __reduce_max_sync(0xffffffffu, mymax);
-  if ((threadIdx.x & 31) == 0 && mymax) atomicMax(maxmag, mymax);
-}
-static constexpr int IM_T = 64, IM_K = 32;                    // 64x64 outputs per CTA, 4x4 per thread, K tiles of 32
-// Exact integer product tile.  ACC = int64_t when max|A| * max|W| * colsA < 2^62 (the quantised demo: 2^19 * 2^12 * 2^11),
-// else __int128 (always exact for 32-bit operands).
-template <typename ACC>
-__device__ __forceinline__ void i32_matmul_tile(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
-                                                size_t rowsA, size_t colsA, size_t colsB,
-                                                int32_t (*As)[IM_T + 4], int32_t (*Ws)[IM_T]) {
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
-  const size_t row0 = (size_t)blockIdx.y * IM_T, col0 = (size_t)blockIdx.x * IM_T;
-  ACC acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
-  for (size_t k0 = 0; k0 < colsA; k0 += IM_K) {
-    for (int e = threadIdx.x; e < IM_T * IM_K; e += 256) {
-      int r = e / IM_K, k = e % IM_K;                          // A: consecutive threads read consecutive k
-      size_t gr = row0 + r, gk = k0 + k;
-      As[k][r] = (gr < rowsA && gk < colsA) ? A[gr * colsA + gk] : 0;
-      int kk = e / IM_T, c = e % IM_T;                         // W: consecutive threads read consecutive columns
-      size_t gk2 = k0 + kk, gc = col0 + c;
-      Ws[kk][c] = (gk2 < colsA && gc < colsB) ? W[gk2 * colsB + gc] : 0;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int k = 0; k < IM_K; ++k) {
-      const int4 av = *reinterpret_cast<const int4*>(&As[k][ty * 4]);
-      const int4 wv = *reinterpret_cast<const int4*>(&Ws[k][tx * 4]);
-      const int32_t a[4] = {av.x, av.y, av.z, av.w}, w[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += (ACC)((int64_t)a[i] * (int64_t)w[j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      size_t gr = row0 + ty * 4 + i, gc = col0 + tx * 4 + j;
-      if (gr >= rowsA || gc >= colsB) continue;
-      __int128 v = acc[i][j];
-      bool negative = v < 0;
-      unsigned __int128 m = negative ? (unsigned __int128)(-v) : (unsigned __int128)v;
-      Fr r = Fr::zero();
-      r.v[0] = (uint32_t)m; r.v[1] = (uint32_t)(m >> 32); r.v[2] = (uint32_t)(m >> 64); r.v[3] = (uint32_t)(m >> 96);
-      r = to_mont(r);
-      C[gr * colsB + gc] = negative ? neg(r) : r;
-    }
-}
-// info[0] = not-all-small flag, info[1] = max|A|, info[2] = max|W|, info[3] = force the 128-bit accumulator (tuning knob)
-__global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
-                                                    size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ info) {
-  __shared__ __align__(16) int32_t As[IM_K][IM_T + 4];        // [k][row], padded: 16-byte aligned rows, 4-way store conflicts at most
-  __shared__ __align__(16) int32_t Ws[IM_K][IM_T];            // [k][col]
-  if (info[0]) return;                                         // the generic Fr kernel takes over
-  const unsigned long long bound = (unsigned long long)info[1] * (unsigned long long)info[2];
-  if (!info[3] && bound <= (1ull << 62) / (colsA ? colsA : 1)) i32_matmul_tile<long long>(A, W, C, rowsA, colsA, colsB, As, Ws);
-  else i32_matmul_tile<__int128>(A, W, C, rowsA, colsA, colsB, As, Ws);
-}
-
 // relu: Z, sign and the packed decomposition (q: u32 rescaled magnitude, r: u16 = rem_mag | rem_sign << 15)
 __global__ void __launch_bounds__(THREADS) k_relu(const Fr* __restrict__ X, Fr* __restrict__ Z, Fr* __restrict__ sign, uint32_t* __restrict__ qpk,
                                                   uint16_t* __restrict__ rpk, size_t n, uint32_t* __restrict__ bad) {
@@ -626,25 +516,6 @@ int zkdl_float_to_fr(const float* fs, zkdl_fr_t* out, uint32_t rows_in, uint32_t
   size_t total = (size_t)rows_out * cols_out;
   if (total == 0) return ZK_OK;
   ZK_LAUNCH(k_float_to_fr<<<stream_grid(total, THREADS), THREADS, 0, S(stream)>>>(fs, F(out), rows_in, rows_out, cols_in, cols_out));
-  return ZK_OK;
-}
-
-int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t rowsA, size_t colsA, size_t colsB, void* stream) {
-  if (rowsA == 0 || colsB == 0) return ZK_OK;
-  cudaStream_t st = S(stream);
-  Scratch ai, wi, flag; int rc;
-  if ((rc = ai.alloc(sizeof(int32_t) * rowsA * colsA, st))) return rc;
-  if ((rc = wi.alloc(sizeof(int32_t) * colsA * colsB, st))) return rc;
-  if ((rc = flag.alloc(sizeof(uint32_t) * 4, st))) return rc;
-  static const uint32_t force128 = getenv("ZKDL_MM_FORCE128") ? 1u : 0u;                     // tuning knob
-  ZK_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t) * 4, st));
-  if (force128) ZK_CUDA(cudaMemsetAsync(flag.as<uint32_t>() + 3, 1, 1, st));
-  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(F(A), ai.as<int32_t>(), rowsA * colsA, flag.as<uint32_t>(), flag.as<uint32_t>() + 1));
-  ZK_LAUNCH(k_fr_to_i32<<<stream_grid(colsA * colsB, THREADS), THREADS, 0, st>>>(F(B), wi.as<int32_t>(), colsA * colsB, flag.as<uint32_t>(), flag.as<uint32_t>() + 2));
-  dim3 igrid(div_up(colsB, IM_T), div_up(rowsA, IM_T));
-  ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), wi.as<int32_t>(), F(C), rowsA, colsA, colsB, flag.as<uint32_t>()));
-  dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
-  ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, st>>>(F(A), F(B), F(C), rowsA, colsA, colsB, flag.as<uint32_t>()));
   return ZK_OK;
 }
 

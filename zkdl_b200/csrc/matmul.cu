@@ -1,0 +1,361 @@
+// matmul.cu — the quantised forward product zkFC::operator() (/root/reference/zkfc.cu:6-47,117-126):
+// C[rowsA x colsB] = A[rowsA x colsA] * W[colsA x colsB] over Fr, bit-identical to the reference's Montgomery dot products.
+//
+// Three kernels, routed on the device (no host synchronisation) by what the operands contain:
+//   k_tc_matmul   operands are small signed integers (|a| < 2^23, |w| < 2^15: the demo's 2^16-scaled activations and
+//                 weights): byte planes on the int8 tensor cores (mma.sync m16n8k32, s32 accumulators per byte shift),
+//                 exact because every partial sum stays below 2^31; needs the prepared weight copy (zkdl_mm_weights)
+//   k_i32_matmul  operands fit int32: SIMT integer dot products, 64-bit accumulators when max|A| max|W| K < 2^62, else 128-bit
+//   k_fr_matmul   anything else: Montgomery products in Fr
+// The exact integer dot product reduced mod p is the same field element as the Fr dot product, so all three agree.
+// The forward pass is outside the reference's timed region (demo.cu:124-138) and inside bench.py's e2e leg.
+#include <atomic>
+#include <stdlib.h>
+#include "common.cuh"
+#include "fr_device.cuh"
+#include "../../include/zkdl_b200.h"
+
+struct zkdl_mm_weights {
+  size_t rows, cols;            // K x N
+  int32_t* w32;                 // [K][N]
+  uint8_t* planes;              // [2][N][K] (W transposed, K contiguous) or nullptr when the shape does not tile
+  uint32_t* info;               // device: {not-small flag, 0, max|w|, 0}
+};
+
+namespace zk {
+extern std::atomic<uint64_t> g_launches;
+#define ZK_LAUNCH(...)            \
+  do {                            \
+    __VA_ARGS__;                  \
+    zk::g_launches.fetch_add(1);  \
+    ZK_CHECK_LAUNCH();            \
+  } while (0)
+
+static constexpr int THREADS = 256;
+static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const Fr* F(const zkdl_fr_t* p) { return reinterpret_cast<const Fr*>(p); }
+static inline Fr* F(zkdl_fr_t* p) { return reinterpret_cast<Fr*>(p); }
+static inline unsigned stream_grid(size_t work_items, int threads) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks ? blocks : 1);
+}
+
+static constexpr int MM_TILE = 16;
+// C = A * B over Fr; 16x16 output tile per CTA, K-tiles staged through shared memory.
+__global__ void __launch_bounds__(MM_TILE * MM_TILE) k_fr_matmul(const Fr* __restrict__ A, const Fr* __restrict__ B, Fr* __restrict__ C,
+                                                                 size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ only_if) {
+  if (only_if && *only_if == 0) return;                      // the small-integer fast path already produced C
+  __shared__ Fr As[MM_TILE][MM_TILE];
+  __shared__ Fr Bs[MM_TILE][MM_TILE];
+  const int tx = threadIdx.x % MM_TILE, ty = threadIdx.x / MM_TILE;
+  const size_t row = (size_t)blockIdx.y * MM_TILE + ty, col = (size_t)blockIdx.x * MM_TILE + tx;
+  Fr sum = Fr::zero();
+  for (size_t k0 = 0; k0 < colsA; k0 += MM_TILE) {
+    As[ty][tx] = (row < rowsA && k0 + tx < colsA) ? A[row * colsA + k0 + tx] : Fr::zero();
+    Bs[ty][tx] = (k0 + ty < colsA && col < colsB) ? B[(k0 + ty) * colsB + col] : Fr::zero();
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < MM_TILE; ++k) sum = add(sum, mul(As[ty][k], Bs[k][tx]));
+    __syncthreads();
+  }
+  if (row < rowsA && col < colsB) C[row * colsB + col] = sum;
+}
+
+// ---- small-integer fast path of the forward matmul.  Quantised activations and weights are Montgomery forms of small
+// signed integers (|v| < 2^31: inputs at scale 2^16, rescaled activations are u32 magnitudes, zkrelu.cu:29).  The exact
+// integer dot product (128-bit accumulator) reduced mod p is the same field element as the Fr dot product, so the result
+// is bit-identical; ~5 integer instructions per multiply-add instead of a 136-IMAD Montgomery product.  Any operand
+// outside the range raises `flag`, and the generic Fr kernel (launched right after, exiting early otherwise) recomputes.
+// flag[0] |= 1 if an element is not a 32-bit signed integer; *maxmag = max |element| (decides the accumulator width)
+// PLANES > 0: also the low PLANES bytes of the two's-complement value as byte planes (planes[p * n + i]), the operand
+// layout of the int8 tensor-core kernel below.
+template <int PLANES>
+__global__ void __launch_bounds__(THREADS) k_fr_to_i32(const Fr* __restrict__ in, int32_t* __restrict__ out, size_t n, uint32_t* __restrict__ flag,
+                                                       uint32_t* __restrict__ maxmag, uint8_t* __restrict__ planes) {
+  uint32_t mymax = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = from_mont(in[i]);
+    bool hi0 = (x.v[1] | x.v[2] | x.v[3] | x.v[4] | x.v[5] | x.v[6] | x.v[7]) == 0;
+    int32_t r = 0;
+    if (hi0 && x.v[0] < 0x80000000u) r = (int32_t)x.v[0];
+    else {
+      Fr m = sub(Fr::zero(), x);                              // p - x
+      bool mhi0 = (m.v[1] | m.v[2] | m.v[3] | m.v[4] | m.v[5] | m.v[6] | m.v[7]) == 0;
+      if (mhi0 && m.v[0] <= 0x80000000u) r = (int32_t)(0u - m.v[0]);
+      else atomicOr(flag, 1u);
+    }
+    out[i] = r;
+#pragma unroll
+    for (int p = 0; p < PLANES; ++p) planes[(size_t)p * n + i] = (uint8_t)((uint32_t)r >> (8 * p));
+    uint32_t mag = r < 0 ? 0u - (uint32_t)r : (uint32_t)r;
+    if (mag > mymax) mymax = mag;
+  }
+  mymax = __reduce_max_sync(0xffffffffu, mymax);
+  if ((threadIdx.x & 31) == 0 && mymax) atomicMax(maxmag, mymax);
+}
+static constexpr int IM_T = 64, IM_K = 32;                    // 64x64 outputs per CTA, 4x4 per thread, K tiles of 32
+// Exact integer product tile.  ACC = int64_t when max|A| * max|W| * colsA < 2^62 (the quantised demo: 2^19 * 2^12 * 2^11),
+// else __int128 (always exact for 32-bit operands).
+template <typename ACC>
+__device__ __forceinline__ void i32_matmul_tile(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
+                                                size_t rowsA, size_t colsA, size_t colsB,
+                                                int32_t (*As)[IM_T + 4], int32_t (*Ws)[IM_T]) {
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const size_t row0 = (size_t)blockIdx.y * IM_T, col0 = (size_t)blockIdx.x * IM_T;
+  ACC acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+  for (size_t k0 = 0; k0 < colsA; k0 += IM_K) {
+    for (int e = threadIdx.x; e < IM_T * IM_K; e += 256) {
+      int r = e / IM_K, k = e % IM_K;                          // A: consecutive threads read consecutive k
+      size_t gr = row0 + r, gk = k0 + k;
+      As[k][r] = (gr < rowsA && gk < colsA) ? A[gr * colsA + gk] : 0;
+      int kk = e / IM_T, c = e % IM_T;                         // W: consecutive threads read consecutive columns
+      size_t gk2 = k0 + kk, gc = col0 + c;
+      Ws[kk][c] = (gk2 < colsA && gc < colsB) ? W[gk2 * colsB + gc] : 0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < IM_K; ++k) {
+      const int4 av = *reinterpret_cast<const int4*>(&As[k][ty * 4]);
+      const int4 wv = *reinterpret_cast<const int4*>(&Ws[k][tx * 4]);
+      const int32_t a[4] = {av.x, av.y, av.z, av.w}, w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += (ACC)((int64_t)a[i] * (int64_t)w[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      size_t gr = row0 + ty * 4 + i, gc = col0 + tx * 4 + j;
+      if (gr >= rowsA || gc >= colsB) continue;
+      __int128 v = acc[i][j];
+      bool negative = v < 0;
+      unsigned __int128 m = negative ? (unsigned __int128)(-v) : (unsigned __int128)v;
+      Fr r = Fr::zero();
+      r.v[0] = (uint32_t)m; r.v[1] = (uint32_t)(m >> 32); r.v[2] = (uint32_t)(m >> 64); r.v[3] = (uint32_t)(m >> 96);
+      r = to_mont(r);
+      C[gr * colsB + gc] = negative ? neg(r) : r;
+    }
+}
+// info[0] = not-all-small flag, info[1] = max|A|, info[2] = max|W|, info[3] = force the 128-bit accumulator (tuning knob),
+// info[4] = the tensor-core kernel handles this product (set by k_mm_route)
+__global__ void __launch_bounds__(256) k_i32_matmul(const int32_t* __restrict__ A, const int32_t* __restrict__ W, Fr* __restrict__ C,
+                                                    size_t rowsA, size_t colsA, size_t colsB, const uint32_t* __restrict__ info) {
+  __shared__ __align__(16) int32_t As[IM_K][IM_T + 4];        // [k][row], padded: 16-byte aligned rows, 4-way store conflicts at most
+  __shared__ __align__(16) int32_t Ws[IM_K][IM_T];            // [k][col]
+  if (info[0] || info[4]) return;                              // the generic Fr kernel / the tensor-core kernel takes over
+  const unsigned long long bound = (unsigned long long)info[1] * (unsigned long long)info[2];
+  if (!info[3] && bound <= (1ull << 62) / (colsA ? colsA : 1)) i32_matmul_tile<long long>(A, W, C, rowsA, colsA, colsB, As, Ws);
+  else i32_matmul_tile<__int128>(A, W, C, rowsA, colsA, colsB, As, Ws);
+}
+
+
+// ---- int8 tensor-core path.  a = a2 * 2^16 + a1 * 2^8 + a0 (a2 signed, a1, a0 unsigned bytes; |a| < 2^23),
+// w = w1 * 2^8 + w0 (w1 signed, w0 unsigned; |w| < 2^15).  The six byte-plane products are accumulated per shift
+// s = i + j in separate s32 accumulators: at most 2 products x 255 x 255 x K < 2^31 for K <= 16384.
+static constexpr int TC_A_PLANES = 3, TC_W_PLANES = 2, TC_SHIFTS = 4;
+static constexpr int TC_M = 64, TC_N = 64, TC_K = 64;          // CTA tile; 8 warps: 4 row blocks of 16 x 2 column blocks of 32
+static constexpr int TC_STRIDE = TC_K + 16;                    // smem row stride (bytes): 20 words, conflict-free fragment loads
+static constexpr uint32_t TC_A_LIMIT = 1u << 23, TC_W_LIMIT = 1u << 15;
+static constexpr size_t TC_MAX_K = 16384;
+
+template <bool SA, bool SB>
+__device__ __forceinline__ void mma_i8(int32_t (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  if (SA && SB)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else if (SA)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else if (SB)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  else
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// info[4] = 1 iff the tensor-core kernel takes this product (operands small enough); evaluated once, on the device
+__global__ void k_mm_route(uint32_t* __restrict__ info, int have_planes) {
+  info[4] = (have_planes && !info[0] && !info[3] && info[1] < TC_A_LIMIT && info[2] < TC_W_LIMIT) ? 1u : 0u;
+}
+
+// Ap: [3][M][K] byte planes of A, Wp: [2][N][K] byte planes of W^T.  M % 64 == 0, N % 64 == 0, K % 64 == 0.
+__global__ void __launch_bounds__(256) k_tc_matmul(const uint8_t* __restrict__ Ap, const uint8_t* __restrict__ Wp, Fr* __restrict__ C,
+                                                   size_t M, size_t K, size_t N, const uint32_t* __restrict__ info) {
+  if (!info[4]) return;
+  __shared__ __align__(16) uint8_t As[TC_A_PLANES][TC_M][TC_STRIDE];
+  __shared__ __align__(16) uint8_t Ws[TC_W_PLANES][TC_N][TC_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+  const size_t row0 = (size_t)blockIdx.y * TC_M, col0 = (size_t)blockIdx.x * TC_N;
+  int32_t acc[TC_SHIFTS][4][4];
+#pragma unroll
+  for (int s = 0; s < TC_SHIFTS; ++s)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[s][j][e] = 0;
+  for (size_t k0 = 0; k0 < K; k0 += TC_K) {
+    // 16-byte chunks: A 3 x 64 rows x 4, W 2 x 64 rows x 4
+    for (int c = threadIdx.x; c < (TC_A_PLANES + TC_W_PLANES) * 64 * 4; c += 256) {
+      const int plane = c / 256, r = (c % 256) / 4, q = c % 4;
+      if (plane < TC_A_PLANES) {
+        const int4 v = *reinterpret_cast<const int4*>(Ap + ((size_t)plane * M + row0 + r) * K + k0 + q * 16);
+        *reinterpret_cast<int4*>(&As[plane][r][q * 16]) = v;
+      } else {
+        const int pw = plane - TC_A_PLANES;
+        const int4 v = *reinterpret_cast<const int4*>(Wp + ((size_t)pw * N + col0 + r) * K + k0 + q * 16);
+        *reinterpret_cast<int4*>(&Ws[pw][r][q * 16]) = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TC_K; kk += 32) {
+      uint32_t a[TC_A_PLANES][4], b[TC_W_PLANES][4][2];
+#pragma unroll
+      for (int p = 0; p < TC_A_PLANES; ++p) {
+        a[p][0] = *reinterpret_cast<const uint32_t*>(&As[p][wm + g][kk + t * 4]);
+        a[p][1] = *reinterpret_cast<const uint32_t*>(&As[p][wm + g + 8][kk + t * 4]);
+        a[p][2] = *reinterpret_cast<const uint32_t*>(&As[p][wm + g][kk + 16 + t * 4]);
+        a[p][3] = *reinterpret_cast<const uint32_t*>(&As[p][wm + g + 8][kk + 16 + t * 4]);
+      }
+#pragma unroll
+      for (int p = 0; p < TC_W_PLANES; ++p)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          b[p][j][0] = *reinterpret_cast<const uint32_t*>(&Ws[p][wn + j * 8 + g][kk + t * 4]);
+          b[p][j][1] = *reinterpret_cast<const uint32_t*>(&Ws[p][wn + j * 8 + g][kk + 16 + t * 4]);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        mma_i8<false, false>(acc[0][j], a[0], b[0][j]);
+        mma_i8<false, false>(acc[1][j], a[1], b[0][j]);
+        mma_i8<false, true>(acc[1][j], a[0], b[1][j]);
+        mma_i8<true, false>(acc[2][j], a[2], b[0][j]);
+        mma_i8<false, true>(acc[2][j], a[1], b[1][j]);
+        mma_i8<true, true>(acc[3][j], a[2], b[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const size_t gr = row0 + wm + g + (e >> 1) * 8, gc = col0 + wn + j * 8 + t * 2 + (e & 1);
+      long long v = 0;
+#pragma unroll
+      for (int s = TC_SHIFTS - 1; s >= 0; --s) v = v * 256 + (long long)acc[s][j][e];     // |v| < 2^29 * 2^24 * 1.01
+      const bool negative = v < 0;
+      const unsigned long long m = negative ? (unsigned long long)(-v) : (unsigned long long)v;
+      Fr r = Fr::zero();
+      r.v[0] = (uint32_t)m; r.v[1] = (uint32_t)(m >> 32);
+      r = to_mont(r);
+      C[gr * N + gc] = negative ? neg(r) : r;
+    }
+}
+
+// W^T byte planes from the int32 copy: planes[(p * N + n) * K + k] = byte p of W[k][n]
+__global__ void __launch_bounds__(THREADS) k_w_planes(const int32_t* __restrict__ w32, uint8_t* __restrict__ planes, size_t K, size_t N) {
+  const size_t total = K * N;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = i / N, n = i - k * N;
+    const uint32_t v = (uint32_t)w32[i];
+#pragma unroll
+    for (int p = 0; p < TC_W_PLANES; ++p) planes[((size_t)p * N + n) * K + k] = (uint8_t)(v >> (8 * p));
+  }
+}
+
+static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr* C, size_t rowsA, size_t colsA, size_t colsB, cudaStream_t st) {
+  Scratch ai, wi, info, ap; int rc;
+  const bool tc_shape = prep && prep->planes && rowsA % TC_M == 0;
+  if ((rc = ai.alloc(sizeof(int32_t) * rowsA * colsA, st))) return rc;
+  if ((rc = info.alloc(sizeof(uint32_t) * 8, st))) return rc;
+  static const uint32_t force128 = getenv("ZKDL_MM_FORCE128") ? 1u : 0u;                     // tuning knobs
+  static const bool no_tc = getenv("ZKDL_MM_NO_TC") != nullptr;
+  uint32_t* inf = info.as<uint32_t>();
+  ZK_CUDA(cudaMemsetAsync(inf, 0, sizeof(uint32_t) * 8, st));
+  if (force128) ZK_CUDA(cudaMemsetAsync(inf + 3, 1, 1, st));
+  const int32_t* w32;
+  if (prep) {
+    ZK_CUDA(cudaMemcpyAsync(inf, prep->info, sizeof(uint32_t) * 3, cudaMemcpyDeviceToDevice, st));   // weight flag and max|w|
+    w32 = prep->w32;
+  } else {
+    if ((rc = wi.alloc(sizeof(int32_t) * colsA * colsB, st))) return rc;
+    ZK_LAUNCH(k_fr_to_i32<0><<<stream_grid(colsA * colsB, THREADS), THREADS, 0, st>>>(W, wi.as<int32_t>(), colsA * colsB, inf, inf + 2, nullptr));
+    w32 = wi.as<int32_t>();
+  }
+  if (tc_shape && !no_tc) {
+    if ((rc = ap.alloc(TC_A_PLANES * rowsA * colsA, st))) return rc;
+    ZK_LAUNCH(k_fr_to_i32<TC_A_PLANES><<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(A, ai.as<int32_t>(), rowsA * colsA, inf, inf + 1, ap.as<uint8_t>()));
+    ZK_LAUNCH(k_mm_route<<<1, 1, 0, st>>>(inf, 1));
+    dim3 tgrid(div_up(colsB, TC_N), div_up(rowsA, TC_M));
+    ZK_LAUNCH(k_tc_matmul<<<tgrid, 256, 0, st>>>(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf));
+  } else {
+    ZK_LAUNCH(k_fr_to_i32<0><<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(A, ai.as<int32_t>(), rowsA * colsA, inf, inf + 1, nullptr));
+  }
+  dim3 igrid(div_up(colsB, IM_T), div_up(rowsA, IM_T));
+  ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), w32, C, rowsA, colsA, colsB, inf));
+  dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
+  ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, st>>>(A, W, C, rowsA, colsA, colsB, inf));
+  return ZK_OK;
+}
+
+}  // namespace zk
+
+using namespace zk;
+
+extern "C" {
+
+int zkdl_fr_matmul(const zkdl_fr_t* A, const zkdl_fr_t* B, zkdl_fr_t* C, size_t rowsA, size_t colsA, size_t colsB, void* stream) {
+  if (rowsA == 0 || colsB == 0) return ZK_OK;
+  ZK_REQUIRE(A && B && C, ZK_ERR_ARG, "null argument");
+  return matmul_run(F(A), F(B), nullptr, F(C), rowsA, colsA, colsB, S(stream));
+}
+
+int zkdl_mm_weights_create(const zkdl_fr_t* W, size_t rows, size_t cols, zkdl_mm_weights** out, void* stream) {
+  cudaStream_t st = S(stream);
+  ZK_REQUIRE(W && out && rows > 0 && cols > 0, ZK_ERR_ARG, "bad weight arguments");
+  zkdl_mm_weights* p = new zkdl_mm_weights();
+  p->rows = rows; p->cols = cols; p->w32 = nullptr; p->planes = nullptr; p->info = nullptr;
+  const bool tiles = rows % TC_K == 0 && cols % TC_N == 0 && rows <= TC_MAX_K;
+  cudaError_t e = cudaMalloc(&p->w32, sizeof(int32_t) * rows * cols);
+  if (e == cudaSuccess) e = cudaMalloc(&p->info, sizeof(uint32_t) * 4);
+  if (e == cudaSuccess && tiles) e = cudaMalloc(&p->planes, (size_t)TC_W_PLANES * rows * cols);
+  if (e != cudaSuccess) { zkdl_mm_weights_destroy(p); set_last_error("cudaMalloc weights: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  e = cudaMemsetAsync(p->info, 0, sizeof(uint32_t) * 4, st);
+  if (e != cudaSuccess) { zkdl_mm_weights_destroy(p); set_last_error("memset: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  k_fr_to_i32<0><<<stream_grid(rows * cols, THREADS), THREADS, 0, st>>>(F(W), p->w32, rows * cols, p->info, p->info + 2, nullptr);
+  if (tiles) k_w_planes<<<stream_grid(rows * cols, THREADS), THREADS, 0, st>>>(p->w32, p->planes, rows, cols);
+  zk::g_launches.fetch_add(tiles ? 2 : 1);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { zkdl_mm_weights_destroy(p); set_last_error("weight kernels: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  *out = p;
+  return ZK_OK;
+}
+
+int zkdl_mm_weights_destroy(zkdl_mm_weights* p) {
+  if (!p) return ZK_OK;
+  cudaFree(p->w32); cudaFree(p->planes); cudaFree(p->info);
+  delete p;
+  return ZK_OK;
+}
+
+int zkdl_fr_matmul_prepared(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_mm_weights* prep, zkdl_fr_t* C, size_t rowsA, void* stream) {
+  ZK_REQUIRE(prep, ZK_ERR_ARG, "null argument");
+  if (rowsA == 0) return ZK_OK;
+  ZK_REQUIRE(A && W && C, ZK_ERR_ARG, "null argument");
+  return matmul_run(F(A), F(W), prep, F(C), rowsA, prep->rows, prep->cols, S(stream));
+}
+
+}  // extern "C"

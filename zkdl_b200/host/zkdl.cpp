@@ -364,9 +364,14 @@ FrTensor zkFC::operator()(const FrTensor& X) const {                            
   if (X.size % inputSize != 0) throw std::runtime_error("Incompatible dimensions");
   uint B = X.size / inputSize;
   FrTensor out(B * outputSize);
-  check(zkdl_fr_matmul(X.gpu_data, weights.gpu_data, out.gpu_data, B, inputSize, outputSize, st())); sync();
+  if (!mm_) {                                     // weights never change after construction: derive the integer copy once
+    mm_ = std::make_shared<MMHolder>();
+    check(zkdl_mm_weights_create(weights.gpu_data, inputSize, outputSize, &mm_->w, st()));
+  }
+  check(zkdl_fr_matmul_prepared(X.gpu_data, weights.gpu_data, mm_->w, out.gpu_data, B, st())); sync();
   return out;
 }
+zkFC::MMHolder::~MMHolder() { if (w) zkdl_mm_weights_destroy(w); }
 void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) const {                                  // zkfc.cu:128-145
   if (X.size % inputSize != 0) throw std::runtime_error("Incompatible dimensions 1");
   uint B = X.size / inputSize;

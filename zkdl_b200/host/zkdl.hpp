@@ -201,6 +201,8 @@ class zkFC {
   G1TensorJacobian com;
   mutable std::vector<Fr_t> proof_fr_;
   mutable std::vector<G1Jacobian_t> proof_g1_;
+  struct MMHolder { zkdl_mm_weights* w = nullptr; ~MMHolder(); };
+  mutable std::shared_ptr<MMHolder> mm_;         // quantised integer copy of `weights` for operator(), shared by copies
  public:
   const uint inputSize;
   const uint outputSize;

@@ -47,6 +47,7 @@ class MLPProver:
             L.W = zk.fr_elementwise(zk.OP_MONT, q, out=q)
             L.com = zk.commit(L.gens, L.W)                                                   # zkfc.cu:102
             L.com_table = zk.G1Table(L.com, full=True)
+            L.mm = zk.MatmulWeights(L.W, L.I, L.O)                                           # integer copy for the forward product
             self.layers.append(L)
         self.n_params = sum(L.in_dim * L.out_dim for L in self.layers)
         torch.cuda.synchronize()
@@ -61,7 +62,7 @@ class MLPProver:
         self.Z, self.A, self.aux = [], [], []
         cur = self.X
         for i, L in enumerate(self.layers):
-            z = zk.fr_matmul(cur, L.W, B, L.I, L.O)
+            z = zk.fr_matmul_prepared(cur, L.mm, B)
             self.Z.append(z)
             if i + 1 < len(self.layers):
                 a, sign, mag, rem, bad = zk.relu_packed(z)                                  # aux kept bit-packed
