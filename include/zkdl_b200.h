@@ -152,13 +152,15 @@ int zkdl_zkrelu_prove_packed(const zkdl_fr_t* X, const zkdl_fr_t* sign, const ui
 /* The same provers restricted to some of their independent parts (sub-layer partition over GPUs).  Only the
  * selected segments of the proof buffers are written; a rank that owns a part passes the full-size buffers and ships
  * its segments.  zkFC: ZKDL_FC_SUMCHECK = [ip sumcheck][Z(u)], ZKDL_FC_OPENING = [open ret] + all of proof_g1.
- * zkReLU: ZKDL_RELU_MAG = [bin(mag)][mag.partial_me], ZKDL_RELU_REM = [bin(rem)][rem.partial_me], ZKDL_RELU_HP = [hadamard]. */
+ * zkReLU: ZKDL_RELU_MAG = [bin(mag)][mag.partial_me], ZKDL_RELU_REM = [bin(rem)][rem.partial_me], ZKDL_RELU_HP = [hadamard].
+ * W_int (may be NULL): the zkdl_mm_weights copy of W; when W is a table of 32-bit integers (quantised weights) the two
+ * weights.partial_me passes (zkfc.cu:139, commitment.cu:88) fold the integers against eq tables: same field elements. */
 #define ZKDL_FC_SUMCHECK 1u
 #define ZKDL_FC_OPENING 2u
 #define ZKDL_RELU_MAG 1u
 #define ZKDL_RELU_REM 2u
 #define ZKDL_RELU_HP 4u
-int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
+int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_mm_weights* W_int, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
                           const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
                           const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
                           zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, unsigned parts, void* stream);

@@ -48,6 +48,30 @@ void hs_digits(const Fr* s, int mont, int c, int W, int32_t* digits, int* sign, 
     if (carry) digits[i * W + W - 1] = 0x7fffffff;   // must never happen (W = ceil(255/c))
   }
 }
+// mixed-width recoding of the full-table MSM: windows [0, nfull) are c bits wide, the rest ctop bits (msm.cu, MsmCfg)
+void hs_digits_mixed(const Fr* s, int mont, int c, int nfull, int ctop, int W, int32_t* digits, int* sign, size_t n) {
+  for (size_t i = 0; i < n; ++i) {
+    Fr mag; bool neg; scalar_prepare(s[i], mont != 0, mag, neg); sign[i] = neg;
+    uint32_t carry = 0;
+    for (int w = 0; w < W; ++w) {
+      int bit = w < nfull ? w * c : nfull * c + (w - nfull) * ctop;
+      digits[i * W + w] = next_digit_at(mag, bit, w < nfull ? c : ctop, carry);
+    }
+    if (carry) digits[i * W + W - 1] = 0x7fffffff;
+  }
+}
+// integer-weighted sums: out[i] = sum_t w[i*k+t] * e[i*k+t] mod p through the 320-bit accumulators (matmul.cu weight folds)
+void hs_isum(const int32_t* w, const Fr* e, Fr* o, size_t n, size_t k) {
+  for (size_t i = 0; i < n; ++i) {
+    ISum pos, neg, pos2; isum_zero(pos); isum_zero(neg); isum_zero(pos2);
+    for (size_t t = 0; t < k; ++t) {
+      int32_t v = w[i * k + t];
+      if (v >= 0) isum_mac((t & 1) ? pos2 : pos, (uint32_t)v, e[i * k + t]); else isum_mac(neg, 0u - (uint32_t)v, e[i * k + t]);
+    }
+    isum_add(pos, pos2);
+    o[i] = sub(isum_reduce(pos), isum_reduce(neg));
+  }
+}
 // G1: XYZZ formulas through the Jacobian PODs
 static G1Jac J(const uint32_t* p) { G1Jac r; for (int i = 0; i < 12; ++i) { r.x.v[i] = p[i]; r.y.v[i] = p[12 + i]; r.z.v[i] = p[24 + i]; } return r; }
 static void S(uint32_t* p, const G1Jac& r) { for (int i = 0; i < 12; ++i) { p[i] = r.x.v[i]; p[12 + i] = r.y.v[i]; p[24 + i] = r.z.v[i]; } }

@@ -125,6 +125,37 @@ def test_signed_digit_recoding(hs, c):
             assert got <= (orc.FR_P - 1) // 2
 
 
+def test_mixed_width_recoding(hs):
+    """20 x 12-bit + 2 x 8-bit windows (full-table MSM with c = 12): digits recompose to the scalar, the top window is spread."""
+    c, nfull, ctop, W = 12, 20, 8, 22
+    vals = [int.from_bytes(rng.bytes(40), "little") % orc.FR_P for _ in range(300)] + [0, 1, orc.FR_P - 1, (orc.FR_P - 1) // 2, (orc.FR_P + 1) // 2]
+    s = orc.to_limbs(vals, 8)
+    d = np.zeros((len(vals), W), np.int32); sg = np.zeros(len(vals), np.int32)
+    hs.hs_digits_mixed(p(s), 0, c, nfull, ctop, W, p(d), p(sg), C.c_size_t(len(vals)))
+    pos = [c * w if w < nfull else nfull * c + (w - nfull) * ctop for w in range(W)]
+    for v, row, neg in zip(vals, d, sg):
+        assert all(abs(int(t)) <= (1 << ((c if w < nfull else ctop) - 1)) for w, t in enumerate(row))
+        got = sum(int(t) << pos[w] for w, t in enumerate(row))
+        assert (-got if neg else got) % orc.FR_P == v and got <= (orc.FR_P - 1) // 2
+    assert len({int(r[-1]) for r in d}) > 16                # the top window carries 6 bits, not 2
+
+
+@pytest.mark.parametrize("k", [1, 7, 2048])
+def test_integer_weighted_sums(hs, k):
+    n = 12
+    w = rng.integers(-(1 << 31), 1 << 31, size=n * k, dtype=np.int64).astype(np.int32)
+    w[:4] = [-(1 << 31), (1 << 31) - 1, 0, -1][: min(4, n * k)] if n * k >= 4 else w[:4]
+    e = rand(n * k - 5, 8)
+    if k >= 7:
+        e[:k] = orc.to_limbs([orc.FR_P - 1] * k); w[:k] = (1 << 31) - 1          # largest positive sum
+        e[k: 2 * k] = orc.to_limbs([orc.FR_P - 1] * k); w[k: 2 * k] = -(1 << 31)   # largest negative sum
+    o = np.zeros((n, 8), np.uint32)
+    hs.hs_isum(p(w), p(e), p(o), C.c_size_t(n), C.c_size_t(k))
+    ei = orc.from_limbs(e)
+    exp = [sum(int(w[i * k + t]) * ei[i * k + t] for t in range(k)) % orc.FR_P for i in range(n)]
+    assert orc.from_limbs(o) == exp
+
+
 def test_g1_xyzz_formulas_match_oracle(hs):
     G = orc.g1_generator()
     ks = orc.to_limbs([int.from_bytes(rng.bytes(31), "little") for _ in range(12)])

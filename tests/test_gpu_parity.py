@@ -278,6 +278,11 @@ def test_zkfc_prove_and_open(zk, B, I, O):
     # sumcheck self-consistency: 2 c0 + c1 + c2 of round 0 equals Z(u_out || u_bs)  
     c = orc.fr_to_ints(pfr[:3])
     assert (2 * c[0] + c[1] + c[2]) % orc.FR_P == orc.fr_to_ints(pfr[nip:nip + 1])[0]
+    # with the integer copy of the weights both weights.partial_me passes fold integers against eq tables: same proof
+    prep = zk.MatmulWeights(dW, I, O)
+    pfr2, pg12 = zk.zkfc_prove(zk.to_device(X), dW, zk.to_device(Z), B, I, O, gens, com_tab, u_bs, u_in, u_out, w_int=prep)
+    assert eq(zk.to_host(pfr2), pfr) and orc.g1_eq(zk.to_host(pg12), pg1).all()
+    prep.close()
     gens.close(); com_tab.close()
 
 

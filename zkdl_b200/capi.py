@@ -383,7 +383,7 @@ FC_SUMCHECK, FC_OPENING = 1, 2                   # ZKDL_FC_* / ZKDL_RELU_* part 
 RELU_MAG, RELU_REM, RELU_HP = 1, 2, 4
 
 
-def zkfc_prove(X, W, Z, B, I, O, gens, com_table, u_bs, u_in, u_out, parts=FC_SUMCHECK | FC_OPENING):
+def zkfc_prove(X, W, Z, B, I, O, gens, com_table, u_bs, u_in, u_out, parts=FC_SUMCHECK | FC_OPENING, w_int=None):
     """zkFC::prove; `parts` restricts it to the sumcheck and/or the opening (only those proof segments are written)."""
     nfr, ng1 = C.c_size_t(0), C.c_size_t(0)
     lib().zkdl_zkfc_proof_sizes(_sz(B), _sz(I), _sz(O), _sz(gens.n), C.byref(nfr), C.byref(ng1))
@@ -391,7 +391,8 @@ def zkfc_prove(X, W, Z, B, I, O, gens, com_table, u_bs, u_in, u_out, parts=FC_SU
     k1, p1 = _host_fr(u_bs if len(u_bs) else None)
     k2, p2 = _host_fr(u_in)
     k3, p3 = _host_fr(u_out)
-    _check(lib().zkdl_zkfc_prove_parts(_ptr(X), _ptr(W), _ptr(Z), _sz(B), _sz(I), _sz(O), gens.handle, com_table.handle, p1, p2, p3,
+    wi = w_int.handle if w_int is not None else C.c_void_p(0)
+    _check(lib().zkdl_zkfc_prove_parts(_ptr(X), _ptr(W), wi, _ptr(Z), _sz(B), _sz(I), _sz(O), gens.handle, com_table.handle, p1, p2, p3,
                                        _ptr(pfr), _ptr(pg1), C.c_uint(parts), _stream()))
     return pfr, pg1
 

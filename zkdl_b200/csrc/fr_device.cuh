@@ -38,6 +38,27 @@ ZK_HD Fr bin_pair(const Fr& a0, const Fr& a1, const Fr& e, const Fr& x, Fr* c) {
   return add(a0, mul(x, d));
 }
 
+// ---- sums of (small integer) x (field element): an unsigned 320-bit accumulator, reduced once at the end.
+// Used to fold a table of quantised weights against an eq table without a Montgomery product per entry:
+// sum_i w_i * E_i mod p with |w_i| < 2^32 is the same field element as the Montgomery sum of products mont(w_i) (x) E_i.
+struct ISum { uint32_t v[10]; };
+ZK_HD void isum_zero(ISum& a) { for (int i = 0; i < 10; ++i) a.v[i] = 0; }
+ZK_HD void isum_mac(ISum& a, uint32_t s, const Fr& e) {            // a += s * e   (up to 2^32 terms before overflow)
+  uint64_t c = 0;
+  for (int j = 0; j < 8; ++j) { uint64_t t = (uint64_t)s * e.v[j] + a.v[j] + c; a.v[j] = (uint32_t)t; c = t >> 32; }
+  uint64_t t = (uint64_t)a.v[8] + c; a.v[8] = (uint32_t)t; a.v[9] += (uint32_t)(t >> 32);
+}
+ZK_HD void isum_add(ISum& a, const ISum& b) {
+  uint64_t c = 0;
+  for (int j = 0; j < 10; ++j) { uint64_t t = (uint64_t)a.v[j] + b.v[j] + c; a.v[j] = (uint32_t)t; c = t >> 32; }
+}
+ZK_HD Fr isum_reduce(const ISum& a) {                               // a mod p
+  Fr lo; for (int j = 0; j < 8; ++j) lo.v[j] = a.v[j];
+  for (int i = 0; i < 5; ++i) final_sub(lo);                        // 2^256 < 5p
+  Fr hi = Fr::zero(); hi.v[0] = a.v[8]; hi.v[1] = a.v[9];
+  return add(lo, to_mont(hi));                                      // hi * 2^256 mod p
+}
+
 // float_to_Fr (/root/reference/zkfc.cu:63-78): round-half-away(|x| * 2^16) as u32 (saturating, NaN -> 0), sign from the
 // sign bit; NOT Montgomery.
 ZK_HD Fr float_to_fr(float x) {

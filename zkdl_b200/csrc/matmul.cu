@@ -20,6 +20,7 @@ struct zkdl_mm_weights {
   int32_t* w32;                 // [K][N]
   uint8_t* planes;              // [2][N][K] (W transposed, K contiguous) or nullptr when the shape does not tile
   uint32_t* info;               // device: {not-small flag, 0, max|w|, 0}
+  bool small;                   // host copy of !flag: every entry is a 32-bit signed integer
 };
 
 namespace zk {
@@ -276,6 +277,90 @@ __global__ void __launch_bounds__(THREADS) k_w_planes(const int32_t* __restrict_
   }
 }
 
+// ---- folds of the quantised weight table against an eq table (zkFC::prove's two weights.partial_me calls, zkfc.cu:139
+// and commitment.cu:88): out = sum_i w_i * E_i with the integers from zkdl_mm_weights, bit-identical to the chain of
+// Fr_partial_me_step folds (a multilinear evaluation is the eq-weighted sum) at ~1/10 of its multiplications.
+int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
+
+__device__ __forceinline__ void isum_mac_signed(ISum& pos, ISum& neg, int32_t w, const Fr& e) {
+  if (w >= 0) isum_mac(pos, (uint32_t)w, e); else isum_mac(neg, 0u - (uint32_t)w, e);
+}
+__device__ __forceinline__ ISum isum_shfl_down(const ISum& a, int d) {
+  ISum r;
+#pragma unroll
+  for (int j = 0; j < 10; ++j) r.v[j] = __shfl_down_sync(0xffffffffu, a.v[j], d);
+  return r;
+}
+// window 1: out[r] = sum_c w[r][c] * E[c]; one warp per row
+__global__ void __launch_bounds__(256) k_wfold_cols(const int32_t* __restrict__ w, const Fr* __restrict__ E, size_t rows, size_t cols, Fr* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (size_t r = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (size_t)gridDim.x * (blockDim.x >> 5)) {
+    ISum pos, neg; isum_zero(pos); isum_zero(neg);
+    const int32_t* row = w + r * cols;
+    for (size_t c = lane; c < cols; c += 32) isum_mac_signed(pos, neg, row[c], E[c]);
+    for (int d = 16; d > 0; d >>= 1) {
+      ISum op = isum_shfl_down(pos, d), on = isum_shfl_down(neg, d);
+      isum_add(pos, op); isum_add(neg, on);
+    }
+    if (lane == 0) out[r] = sub(isum_reduce(pos), isum_reduce(neg));
+  }
+}
+// window W: partial[(s * W + c) * 2 + {0,1}] = sum over the rows of slice s of w[r][c] * E[r]  (pos / neg)
+__global__ void __launch_bounds__(128) k_wfold_rows(const int32_t* __restrict__ w, const Fr* __restrict__ E, size_t rows, size_t W, int slices,
+                                                    ISum* __restrict__ partial) {
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
+  if (c >= W) return;
+  const size_t per = (rows + slices - 1) / slices, r0 = s * per, r1 = r0 + per < rows ? r0 + per : rows;
+  ISum pos, neg; isum_zero(pos); isum_zero(neg);
+  for (size_t r = r0; r < r1; ++r) isum_mac_signed(pos, neg, w[r * W + c], E[r]);
+  partial[((size_t)s * W + c) * 2] = pos;
+  partial[((size_t)s * W + c) * 2 + 1] = neg;
+}
+__global__ void __launch_bounds__(128) k_wfold_rows_final(const ISum* __restrict__ partial, size_t W, int slices, Fr* __restrict__ out) {
+  const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (c >= W) return;
+  ISum pos = partial[c * 2], neg = partial[c * 2 + 1];
+  for (int s = 1; s < slices; ++s) { isum_add(pos, partial[((size_t)s * W + c) * 2]); isum_add(neg, partial[((size_t)s * W + c) * 2 + 1]); }
+  out[c] = sub(isum_reduce(pos), isum_reduce(neg));
+}
+
+bool mmw_usable(const zkdl_mm_weights* p, size_t n) {
+  static const bool off = getenv("ZKDL_NO_WFOLD") != nullptr;                               // tuning knob
+  return p && p->small && !off && p->rows * p->cols == n;
+}
+static int eq_for(const zkdl_fr_t* u_host, size_t k, Scratch& ud, Scratch& E, cudaStream_t st) {
+  int rc;
+  if ((rc = ud.alloc(sizeof(Fr) * (k ? k : 1), st))) return rc;
+  if (k) ZK_CUDA(cudaMemcpyAsync(ud.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << k), st))) return rc;
+  return build_eq_table(ud.as<Fr>(), u_host, (int)k, 0, E.as<Fr>(), st);
+}
+// the table as [n / 2^k][2^k], folded over its columns (FrTensor::partial_me(u, 1)): out has n / 2^k entries
+int wfold_cols(const zkdl_mm_weights* p, const zkdl_fr_t* u_host, size_t k, Fr* out, cudaStream_t st) {
+  const size_t n = p->rows * p->cols, cols = (size_t)1 << k;
+  ZK_REQUIRE(k < 31 && n % cols == 0, ZK_ERR_DIM, "Incompatible dimensions");
+  const size_t rows = n / cols;
+  Scratch ud, E; int rc;
+  if ((rc = eq_for(u_host, k, ud, E, st))) return rc;
+  ZK_LAUNCH(k_wfold_cols<<<(unsigned)((rows + 7) / 8 < 4096 ? (rows + 7) / 8 : 4096), 256, 0, st>>>(p->w32, E.as<Fr>(), rows, cols, out));
+  return ZK_OK;
+}
+// the table as [rows][window], folded over its rows (FrTensor::partial_me(u, window)), rows <= 2^k: out has `window` entries
+int wfold_rows(const zkdl_mm_weights* p, size_t window, const zkdl_fr_t* u_host, size_t k, Fr* out, cudaStream_t st) {
+  const size_t n = p->rows * p->cols;
+  ZK_REQUIRE(k < 31 && window > 0 && n % window == 0 && n / window <= ((size_t)1 << k), ZK_ERR_DIM, "Incompatible dimensions");
+  const size_t rows = n / window;
+  Scratch ud, E, part; int rc;
+  if ((rc = eq_for(u_host, k, ud, E, st))) return rc;
+  int slices = rows >= 32 ? 32 : (int)rows;
+  if ((rc = part.alloc(sizeof(ISum) * 2 * slices * window, st))) return rc;
+  dim3 grid(div_up(window, 128), slices);
+  ZK_LAUNCH(k_wfold_rows<<<grid, 128, 0, st>>>(p->w32, E.as<Fr>(), rows, window, slices, part.as<ISum>()));
+  ZK_LAUNCH(k_wfold_rows_final<<<div_up(window, 128), 128, 0, st>>>(part.as<ISum>(), window, slices, out));
+  return ZK_OK;
+}
+
 static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr* C, size_t rowsA, size_t colsA, size_t colsB, cudaStream_t st) {
   Scratch ai, wi, info, ap; int rc;
   const bool tc_shape = prep && prep->planes && rowsA % TC_M == 0;
@@ -327,7 +412,7 @@ int zkdl_mm_weights_create(const zkdl_fr_t* W, size_t rows, size_t cols, zkdl_mm
   cudaStream_t st = S(stream);
   ZK_REQUIRE(W && out && rows > 0 && cols > 0, ZK_ERR_ARG, "bad weight arguments");
   zkdl_mm_weights* p = new zkdl_mm_weights();
-  p->rows = rows; p->cols = cols; p->w32 = nullptr; p->planes = nullptr; p->info = nullptr;
+  p->rows = rows; p->cols = cols; p->w32 = nullptr; p->planes = nullptr; p->info = nullptr; p->small = false;
   const bool tiles = rows % TC_K == 0 && cols % TC_N == 0 && rows <= TC_MAX_K;
   cudaError_t e = cudaMalloc(&p->w32, sizeof(int32_t) * rows * cols);
   if (e == cudaSuccess) e = cudaMalloc(&p->info, sizeof(uint32_t) * 4);
@@ -338,8 +423,12 @@ int zkdl_mm_weights_create(const zkdl_fr_t* W, size_t rows, size_t cols, zkdl_mm
   k_fr_to_i32<0><<<stream_grid(rows * cols, THREADS), THREADS, 0, st>>>(F(W), p->w32, rows * cols, p->info, p->info + 2, nullptr);
   if (tiles) k_w_planes<<<stream_grid(rows * cols, THREADS), THREADS, 0, st>>>(p->w32, p->planes, rows, cols);
   zk::g_launches.fetch_add(tiles ? 2 : 1);
-  e = cudaGetLastError();
+  uint32_t flag = 1;                                            // set-up time: one read-back tells the host which fold path applies
+  e = cudaMemcpyAsync(&flag, p->info, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { zkdl_mm_weights_destroy(p); set_last_error("weight kernels: %s", cudaGetErrorString(e)); return ZK_ERR_CUDA; }
+  p->small = flag == 0;
   *out = p;
   return ZK_OK;
 }

@@ -570,8 +570,11 @@ static int me_open_run(const zkdl_g1_table* gens, const Fr* t, size_t n, const z
   return msm_run(gens, rows.as<Fr>(), 3 * k + 1, 0, 0, proof, st);
 }
 
-int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr* t, size_t nt, const zkdl_fr_t* u_host, size_t ku,
-             G1Jac* com_eval, G1Jac* proof, Fr* ret, cudaStream_t st) {
+bool mmw_usable(const zkdl_mm_weights* p, size_t n);
+int wfold_rows(const zkdl_mm_weights* p, size_t window, const zkdl_fr_t* u_host, size_t k, Fr* out, cudaStream_t st);
+
+int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr* t, size_t nt, const zkdl_mm_weights* t_int,
+             const zkdl_fr_t* u_host, size_t ku, G1Jac* com_eval, G1Jac* proof, Fr* ret, cudaStream_t st) {
   size_t ncom = com_table->n;
   size_t khi = zkdl_ceil_log2((uint32_t)ncom);
   ZK_REQUIRE(ku >= khi, ZK_ERR_DIM, "Incompatible dimensions");
@@ -600,7 +603,9 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   size_t tf_n = zkdl_partial_me_size(nt, khi, w);
   ZK_REQUIRE(tf_n == w, ZK_ERR_DIM, "Incompatible dimensions");                                         // commitment.cu:64
   if ((rc = tf.alloc(sizeof(Fr) * tf_n, st))) return rc;
-  if ((rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st))) return rc;
+  if (mmw_usable(t_int, nt)) rc = wfold_rows(t_int, w, u_hi, khi, tf.as<Fr>(), st);     // quantised weights: fold the integers
+  else rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st);
+  if (rc) return rc;
   rc = me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
   int rj = ss.join(st);
   return rc ? rc : rj;
@@ -688,7 +693,7 @@ int zkdl_me_open(const zkdl_g1_table* gens, const zkdl_fr_t* t, size_t n, const 
 int zkdl_open(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const zkdl_fr_t* t, size_t nt, const zkdl_fr_t* u_host, size_t ku,
               zkdl_g1_jacobian_t* com_eval, zkdl_g1_jacobian_t* proof, zkdl_fr_t* ret, void* stream) {
   ZK_REQUIRE(gens && com_table && t && com_eval && proof && ret, ZK_ERR_ARG, "null argument");
-  return open_run(gens, com_table, reinterpret_cast<const Fr*>(t), nt, u_host, ku, reinterpret_cast<G1Jac*>(com_eval),
+  return open_run(gens, com_table, reinterpret_cast<const Fr*>(t), nt, nullptr, u_host, ku, reinterpret_cast<G1Jac*>(com_eval),
                   reinterpret_cast<G1Jac*>(proof), reinterpret_cast<Fr*>(ret), S(stream));
 }
 int zkdl_g1_me(const zkdl_g1_jacobian_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, zkdl_g1_jacobian_t* out, void* stream) {

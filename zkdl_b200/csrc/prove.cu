@@ -7,8 +7,10 @@
 
 struct zkdl_g1_table;
 namespace zk {
-int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr* t, size_t nt, const zkdl_fr_t* u_host, size_t ku,
-             G1Jac* com_eval, G1Jac* proof, Fr* ret, cudaStream_t st);
+int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr* t, size_t nt, const zkdl_mm_weights* t_int,
+             const zkdl_fr_t* u_host, size_t ku, G1Jac* com_eval, G1Jac* proof, Fr* ret, cudaStream_t st);
+bool mmw_usable(const zkdl_mm_weights* p, size_t n);
+int wfold_cols(const zkdl_mm_weights* p, const zkdl_fr_t* u_host, size_t k, Fr* out, cudaStream_t st);
 }
 using namespace zk;
 
@@ -26,11 +28,11 @@ int zkdl_zkfc_prove(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, 
                     const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
                     const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
                     zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, void* stream) {
-  return zkdl_zkfc_prove_parts(X, W, Z, B, I, O, gens, com_table, u_bs_host, u_in_host, u_out_host, proof_fr, proof_g1,
+  return zkdl_zkfc_prove_parts(X, W, nullptr, Z, B, I, O, gens, com_table, u_bs_host, u_in_host, u_out_host, proof_fr, proof_g1,
                                ZKDL_FC_SUMCHECK | ZKDL_FC_OPENING, stream);
 }
 
-int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
+int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_mm_weights* W_int, const zkdl_fr_t* Z, size_t B, size_t I, size_t O,
                           const zkdl_g1_table* gens, const zkdl_g1_table* com_table,
                           const zkdl_fr_t* u_bs_host, const zkdl_fr_t* u_in_host, const zkdl_fr_t* u_out_host,
                           zkdl_fr_t* proof_fr, zkdl_g1_jacobian_t* proof_g1, unsigned parts, void* stream) {
@@ -51,7 +53,9 @@ int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_
     if ((rc = Wr.alloc(sizeof(Fr) * I, ss.stream))) return rc;
     // X.partial_me(u_bs, inputSize), weights.partial_me(u_out_dim, 1)   (zkfc.cu:139)
     if ((rc = zkdl_fr_partial_me(X, B * I, u_bs_host, kb, I, Xr.as<zkdl_fr_t>(), sst))) return rc;
-    if ((rc = zkdl_fr_partial_me(W, I * O, u_out_host, ko, 1, Wr.as<zkdl_fr_t>(), sst))) return rc;
+    if (mmw_usable(W_int, I * O)) rc = wfold_cols(W_int, u_out_host, ko, Wr.as<Fr>(), ss.stream);       // same field elements from the integers
+    else rc = zkdl_fr_partial_me(W, I * O, u_out_host, ko, 1, Wr.as<zkdl_fr_t>(), sst);
+    if (rc) return rc;
     if ((rc = zkdl_ip_sumcheck(Xr.as<zkdl_fr_t>(), Wr.as<zkdl_fr_t>(), I, u_in_host, ki, proof_fr, sst))) return rc;
     // Z(u_out || u_bs)   (zkfc.cu:141-143)
     zkdl_fr_t uz[64];
@@ -66,7 +70,7 @@ int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_fr_
     ZK_REQUIRE(ko + ki <= 64, ZK_ERR_DIM, "Incompatible dimensions");
     for (size_t i = 0; i < ko; ++i) uo[i] = u_out_host[i];
     for (size_t i = 0; i < ki; ++i) uo[ko + i] = u_in_host[i];
-    rc = open_run(gens, com_table, reinterpret_cast<const Fr*>(W), I * O, uo, ko + ki, reinterpret_cast<G1Jac*>(proof_g1),
+    rc = open_run(gens, com_table, reinterpret_cast<const Fr*>(W), I * O, W_int, uo, ko + ki, reinterpret_cast<G1Jac*>(proof_g1),
                   reinterpret_cast<G1Jac*>(proof_g1 + 1), reinterpret_cast<Fr*>(proof_fr + nip + 1), st);
     if (rc) return rc;
   }

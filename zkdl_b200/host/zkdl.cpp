@@ -381,8 +381,10 @@ void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) c
   size_t nfr, ng1;
   zkdl_zkfc_proof_sizes(B, inputSize, outputSize, generators.size, &nfr, &ng1);
   FrTensor pfr((uint)nfr); G1TensorJacobian pg1((uint)ng1);
-  check(zkdl_zkfc_prove(X.gpu_data, weights.gpu_data, Z.gpu_data, B, inputSize, outputSize, generators.table(), com.table(),
-                        u_bs.data(), u_in.data(), u_out.data(), pfr.gpu_data, pg1.gpu_data, st()));
+  // the integer copy of the weights exists once operator() has run (the forward pass precedes the proof, demo.cu:116-138)
+  check(zkdl_zkfc_prove_parts(X.gpu_data, weights.gpu_data, mm_ ? mm_->w : nullptr, Z.gpu_data, B, inputSize, outputSize,
+                              generators.table(), com.table(), u_bs.data(), u_in.data(), u_out.data(), pfr.gpu_data, pg1.gpu_data,
+                              ZKDL_FC_SUMCHECK | ZKDL_FC_OPENING, st()));
   sync();
   proof_fr_ = download(pfr);
   proof_g1_.resize(ng1);

@@ -132,7 +132,7 @@ class MLPProver:
             L = self.layers[i]
             if kind == "fc":
                 Xin = self.A[i - 1] if i > 0 else self.X
-                return ("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, *ch, parts=mask)
+                return ("fc", i) + zk.zkfc_prove(Xin, L.W, self.Z[i], B, L.I, L.O, L.gens, L.com_table, *ch, parts=mask, w_int=L.mm)
             sign, mag, rem = self.aux[i]
             return ("relu", i, zk.zkrelu_prove_packed(self.Z[i], sign, mag, rem, *ch, parts=mask))
 
