@@ -1,0 +1,114 @@
+"""prove -> file -> verify for the demo path (the reference drops its proofs and has no verifier).
+
+    python -m zkdl_b200.proof_file prove  --out proof.zkp [--model traced_model.pt --input sample_input.pt] [--seed N]
+    python -m zkdl_b200.proof_file verify proof.zkp
+
+`prove` mirrors ./demo (demo.cu:99-143: load the TorchScript MLP and the input batch, commit, forward, prove) and writes
+the public part (shapes, generators, weight commitments), the challenges and every proof element in the wire format of
+zkdl_b200/serialize.py.  `verify` needs nothing but the file: it re-derives com(u_hi) from the public commitments and
+checks every sumcheck and opening identity (zkdl_b200/verify.py).  Challenges are the prover's injected random_vec
+streams, as in the reference (no Fiat-Shamir transcript: SURVEY.md §0 fact 3), so this checks consistency, not soundness
+against a prover who picks its own challenges."""
+import argparse
+import sys
+import time
+
+import numpy as np
+
+from . import serialize
+
+
+def export(P, proof, path):
+    """P: MLPProver after forward() and prove(); proof: what prove() returned (whole tasks only)."""
+    from . import capi as zk
+    layers = []
+    for L in P.layers:
+        layers.append({"in_dim": L.in_dim, "out_dim": L.out_dim, "I": L.I, "O": L.O,
+                       "generators": zk.to_host(zk.g1_normalize(L.G)), "commitment": zk.to_host(zk.g1_normalize(L.com))})
+    tasks = []
+    for part, (kind, i, ch, mask) in zip(proof, P.last_tasks):
+        if mask != (3 if kind == "fc" else 7):
+            raise ValueError("only whole layer proofs can be exported (assemble the pieces first)")
+        tasks.append({"kind": kind, "layer": i, "challenges": [np.asarray(c, dtype=np.uint32).reshape(-1, 8) for c in ch],
+                      "fr": zk.to_host(part[2]), "g1": zk.to_host(zk.g1_normalize(part[3])) if kind == "fc" else None})
+    blob = serialize.dumps({"batch": P.B, "layers": layers}, tasks)
+    with open(path, "wb") as f:
+        f.write(blob)
+    return len(blob)
+
+
+def verify_file(path):
+    """Raises verify.VerifyError (or ValueError for a malformed file); returns a per-task summary on success."""
+    from . import capi as zk, verify
+    with open(path, "rb") as f:
+        public, tasks = serialize.loads(f.read())
+    B = public["batch"]
+    dev = [{"G": zk.to_device(L["generators"]), "com": zk.to_device(L["commitment"])} for L in public["layers"]]
+    summary = []
+    for t in tasks:
+        L, D = public["layers"][t["layer"]], dev[t["layer"]]
+        fr = zk.to_device(t["fr"])
+        if t["kind"] == "fc":
+            u_bs, u_in, u_out = t["challenges"]
+            g1 = zk.to_device(t["g1"])
+            info = verify.verify_zkfc(fr, g1, D["G"], B, L["I"], L["O"], u_bs, u_in, u_out)
+            u = np.concatenate([u_out.reshape(-1, 8), u_in.reshape(-1, 8)])
+            klo = (D["G"].shape[0] - 1).bit_length()
+            verify.verify_commitment_eval(D["com"], g1[:1], u[klo:])
+            summary.append(("fc", t["layer"], info["z_eval"]))
+        else:
+            u_z, v_z, u_r, v_r, u_rec, u_hp, v_hp = t["challenges"]
+            verify.verify_zkrelu(fr, B * L["O"], u_z, v_z, u_r, v_r, u_hp, v_hp)
+            summary.append(("relu", t["layer"], None))
+    return summary
+
+
+def load_torchscript(model_path, input_path):
+    """The ./demo inputs (demo.cu:48-95): children "0", "1", ... with a bias-free `weight` for Linear layers; the input is
+    a module holding parameter "0"."""
+    import torch
+    m = torch.jit.load(model_path, map_location="cuda")
+    ws = []
+    for _, child in m.named_children():
+        params = dict(child.named_parameters())
+        if "weight" in params:
+            ws.append(params["weight"].detach().t().contiguous().float())
+    x = dict(torch.jit.load(input_path, map_location="cuda").named_parameters())["0"].detach().float()
+    return ws, x
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(prog="python -m zkdl_b200.proof_file")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    pp = sub.add_parser("prove"); pp.add_argument("--out", required=True); pp.add_argument("--model"); pp.add_argument("--input")
+    pp.add_argument("--seed", type=int, default=0); pp.add_argument("--batch", type=int, default=256)
+    pv = sub.add_parser("verify"); pv.add_argument("file")
+    a = ap.parse_args(argv)
+    import torch
+    from . import capi as zk, mlp
+    if not torch.cuda.is_available():
+        sys.exit("zkdl_b200 needs a CUDA device: there is no CPU fallback")
+    zk.lib()
+    if a.cmd == "prove":
+        if a.model:
+            ws, x = load_torchscript(a.model, a.input)
+        else:
+            ws, x = mlp.synthetic_mlp(mlp.demo_layer_dims(), a.batch, seed=0)
+        P = mlp.MLPProver(ws, gen_seed=a.seed + 1)
+        P.forward(x)
+        P.prove(seed=a.seed)                                             # warm-up (scratch arenas)
+        torch.cuda.synchronize(); t0 = time.time()
+        proof = P.prove(seed=a.seed)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        n = export(P, proof, a.out)
+        print(f"Total number of parameters: {P.n_params}")
+        print(f"Proof time: {dt / x.shape[0]} seconds per data point.  {len(proof)} layer proofs, {n} bytes -> {a.out}")
+    else:
+        t0 = time.time()
+        s = verify_file(a.file)
+        print(f"verified {len(s)} layer proofs in {time.time() - t0:.2f} s: " + ", ".join(f"{k}{i}" for k, i, _ in s))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

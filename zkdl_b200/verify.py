@@ -128,6 +128,19 @@ def verify_opening(G, com_eval, open_proof, open_ret, u_lo, gens_table=None):
     return s_final * RINV % P                                          # the opened evaluation W~(u)
 
 
+def verify_commitment_eval(com, com_eval, u_hi):
+    """com(u_hi) (proof_g1[0]) against the PUBLIC row commitments: sum_r eq(u_hi, r) com[r]  (g1-tensor.cu:463-491)."""
+    w = [1]
+    for row in np.asarray(u_hi).reshape(-1, 8):
+        x = plain(row)
+        w = [wb * (1 - x) % P for wb in w] + [wb * x % P for wb in w]
+    _req(com.shape[0] <= len(w), "commitment: more rows than the challenge addresses")
+    tab = zk.G1Table(com, full=False)
+    exp = zk.msm(tab, zk.to_device(int_to_limbs(w[: com.shape[0]])), 1, False)
+    tab.close()
+    _req(_same_point(com_eval, exp), "commitment: com(u_hi) is not the evaluation of the public commitment")
+
+
 def verify_zkfc(proof_fr, proof_g1, G, B, I, O, u_bs, u_in, u_out, gens_table=None):
     """zkFC::prove (zkfc.cu:128-145): proof_fr = [ip][Z(u)][open_ret], proof_g1 = [com(u_hi)][me_open ...]."""
     fr = zk.to_host(proof_fr)
