@@ -207,7 +207,123 @@ static std::vector<Fr_t> seeded_vec(uint len, unsigned seed) {      // random_ve
   return out;
 }
 
+// ------------------------------------------------------------------------------------------------ full
+// Full-size differential cases (BASELINE.json configs 2-5): inputs are regenerated from seeds on both sides (std::mt19937
+// here, numpy's legacy MT19937 seeding in tests/test_fullsize_reference.py), so only the (small) results travel.
+// Signed small integers: v = (mt() & (2^bits - 1)) - 2^(bits-1), Montgomery form.
+static FrTensor rand_signed(uint n, uint bits, unsigned seed) {
+  std::mt19937 mt(seed); std::vector<Fr_t> pos(n), neg(n);
+  const uint mask = (1u << bits) - 1, half = 1u << (bits - 1);
+  for (uint i = 0; i < n; ++i) {
+    uint r = (uint)mt() & mask;
+    pos[i] = {r >= half ? r - half : 0u, 0, 0, 0, 0, 0, 0, 0};
+    neg[i] = {r >= half ? 0u : half - r, 0, 0, 0, 0, 0, 0, 0};
+  }
+  FrTensor P(n, pos.data()), N(n, neg.data());
+  FrTensor t = P - N; t.mont(); return t;
+}
+static G1TensorJacobian seeded_points(uint n, unsigned seed) {      // [k_i] g, k_i = raw limbs of seeded_vec (demo.cu:81-82 pattern)
+  G1TensorJacobian G(n, G1Jacobian_generator);
+  auto ks = seeded_vec(n, seed); FrTensor kt(n, ks.data()); G *= kt; return G;
+}
+static FrTensor forward_product(const FrTensor& X, const FrTensor& W, uint B, uint I, uint O) {
+#ifndef ZKDL_HOST_BUILD
+  // the reference's own kernel (zkfc.cu:6-47), launched as zkFC::operator() does (zkfc.cu:117-126) without paying for
+  // zkFC's constructor (it commits the weights with |W| bit-serial ladders)
+  FrTensor out(B * O);
+  dim3 blockSize(TILE_WIDTH, TILE_WIDTH), gridSize((O + TILE_WIDTH - 1) / TILE_WIDTH, (B + TILE_WIDTH - 1) / TILE_WIDTH);
+  matrixMultiplyOptimized<<<gridSize, blockSize>>>(X.gpu_data, W.gpu_data, out.gpu_data, B, I, O);
+  cudaDeviceSynchronize();
+  return out;
+#else
+  Commitment G1c(64, G1Jacobian_generator);
+  zkFC fc(I, O, W, G1c);
+  return fc(X);
+#endif
+}
+static std::vector<Fr_t> cat(const std::vector<Fr_t>& a, const std::vector<Fr_t>& b) { std::vector<Fr_t> r(a); r.insert(r.end(), b.begin(), b.end()); return r; }
+
+static void full_fc(Box& out, uint I, uint O, uint B, bool with_open, uint wbits) {
+  FrTensor W = rand_signed(I * O, wbits, 1), X = rand_signed(B * I, 17, 2);
+  FrTensor Z = forward_product(X, W, B, I, O);
+  uint kb = ceilLog2(B), ki = ceilLog2(I), ko = ceilLog2(O);
+  auto u_bs = seeded_vec(kb, 101), u_in = seeded_vec(ki, 102), u_out = seeded_vec(ko, 103);
+  FrTensor Xr = X.partial_me(u_bs, I), Wr = W.partial_me(u_out, 1);                // zkfc.cu:139
+  out["fc.xr"] = fr_out(Xr); out["fc.wr"] = fr_out(Wr);
+  out["fc.ip"] = fr_out(inner_product_sumcheck(Xr, Wr, u_in));
+  out["fc.zu"] = fr_out(Z(cat(u_out, u_bs)));                                       // zkfc.cu:141-143
+  out["fc.z_sum"] = fr_out(Z.sum());
+  if (with_open) {
+    uint ng = 1u << ((ceilLog2(I * O) + 1) / 2);                                    // demo.cu:81
+    G1TensorJacobian g0 = seeded_points(ng, 7);
+    std::vector<uint32_t> gw = g1_out(g0);
+    Commitment G(ng, reinterpret_cast<const G1Jacobian_t*>(gw.data()));
+    uint ncom = I * O / ng;
+    G1TensorJacobian com = seeded_points(ncom, 9);                                  // any points: com(u_hi) does not depend on W
+    auto u = cat(u_out, u_in);
+    uint k = ceilLog2(ncom);
+    const std::vector<Fr_t> u_hi(u.end() - k, u.end()), u_lo(u.begin(), u.end() - k);
+    out["open.com_eval"] = g1_out(com(u_hi));                                       // commitment.cu:88
+    FrTensor tf = W.partial_me(u_hi, 1u << u_lo.size());
+    out["open.tf"] = fr_out(tf);
+    std::vector<G1Jacobian_t> proof;
+    Fr_t ret = Commitment::me_open(tf, G, u_lo.begin(), u_lo.end(), proof);         // commitment.cu:91
+    out["open.proof"] = g1_out(proof); out["open.ret"] = fr_out(ret);
+    std::vector<G1Jacobian_t> rows;                                                 // true row commitments of the first rows
+    for (uint r = 0; r < 2; ++r) {
+      std::vector<uint32_t> roww((size_t)ng * 8);
+      cudaMemcpy(roww.data(), W.gpu_data + (size_t)r * ng, roww.size() * 4, cudaMemcpyDeviceToHost);
+      FrTensor row = fr_in(roww); row.unmont();
+      rows.push_back((G * row).sum());
+    }
+    out["open.com_rows"] = g1_out(rows);
+  }
+}
+static void full_relu(Box& out, uint I, uint O, uint B, uint wbits) {
+  FrTensor W = rand_signed(I * O, wbits, 1), X = rand_signed(B * I, 17, 2);
+  FrTensor Z = forward_product(X, W, B, I, O);
+  zkReLU relu; FrTensor A = relu(Z);
+  uint L = ceilLog2(B * O);
+  out["relu.a_me"] = fr_out(A(seeded_vec(L, 201)));
+  out["relu.sign_me"] = fr_out((*relu.sign_ptr)(seeded_vec(L, 202)));
+  out["relu.mag_me"] = fr_out((*relu.mag_bin_ptr)(seeded_vec(L + 5, 203)));
+  out["relu.rem_me"] = fr_out((*relu.rem_bin_ptr)(seeded_vec(L + 4, 204)));
+  auto u_z = seeded_vec(L + 5, 211), v_z = seeded_vec(L + 5, 212), u_r = seeded_vec(L + 4, 213), v_r = seeded_vec(L + 4, 214);
+  auto u_rec = seeded_vec(L, 215), u_hp = seeded_vec(L, 216), v_hp = seeded_vec(L, 217);
+  out["relu.mag_sc"] = fr_out(binary_sumcheck(*relu.mag_bin_ptr, u_z, v_z));        // zkrelu.cu:91-94
+  out["relu.mag_rec"] = fr_out(relu.mag_bin_ptr->partial_me(u_rec, 32));
+  out["relu.rem_sc"] = fr_out(binary_sumcheck(*relu.rem_bin_ptr, u_r, v_r));
+  out["relu.rem_rec"] = fr_out(relu.rem_bin_ptr->partial_me(u_rec, 16));
+  out["relu.hp"] = fr_out(hadamard_product_sumcheck(Z, *relu.sign_ptr, u_hp, v_hp));   // zkrelu.cu:99
+}
+static void full_msm(Box& out, uint k) {
+  uint n = 1u << k;
+  G1TensorJacobian G = seeded_points(n, 7);
+  auto sv = seeded_vec(n, 8); FrTensor s(n, sv.data());
+  out["msm.full"] = g1_out((G * s).sum());                                          // 255-bit scalars
+  FrTensor w = rand_signed(n, 16, 3); w.unmont();                                   // the quantised-weight distribution
+  out["msm.small"] = g1_out((G * w).sum());
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 6 && !strcmp(argv[1], "full")) {
+    Box out; std::string what = argv[2];
+    double t0 = now();
+    if (what == "layer") {              // full <layer> <log_dim> <batch> <out.bin>: one hidden layer, zkFC + zkReLU pieces
+      uint k = atoi(argv[3]), B = atoi(argv[4]);
+      full_fc(out, 1u << k, 1u << k, B, true, 13);
+      full_relu(out, 1u << k, 1u << k, B, 13);
+    } else if (what == "fc") {          // full fc <log_dim> <batch> <out.bin>: config 2, the zkFC sumcheck set
+      uint k = atoi(argv[3]), B = atoi(argv[4]);
+      full_fc(out, 1u << k, 1u << k, B, false, 16);
+    } else if (what == "msm") {         // full msm <log_n> 0 <out.bin>: config 3, (G * s).sum()
+      full_msm(out, atoi(argv[3]));
+    } else { fprintf(stderr, "unknown full case\n"); return 1; }
+    out["cuda_status"] = std::vector<uint32_t>(1, (uint32_t)cudaGetLastError());
+    write_box(argv[5], out);
+    printf("{\"what\":\"full_%s\",\"seconds\":%.3f,\"cuda_status\":%d}\n", what.c_str(), now() - t0, (int)out["cuda_status"][0]);
+    return 0;
+  }
   if (argc >= 4 && !strcmp(argv[1], "run")) {
     Box in = read_box(argv[2]), out;
     run_cases(in, out);
@@ -296,6 +412,6 @@ int main(int argc, char** argv) {
     printf("{\"cuda_status\":%d}\n", (int)cudaGetLastError());
     return 0;
   }
-  fprintf(stderr, "usage: ref_harness run <in> <out> | time <fold|fc|msm|open|relu|layer> <log_n> [reps] [batch]\n");
+  fprintf(stderr, "usage: ref_harness run <in> <out> | time <fold|fc|msm|open|relu|layer> <log_n> [reps] [batch] | full <layer|fc|msm> <log_n> <batch> <out>\n");
   return 1;
 }

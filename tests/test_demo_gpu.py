@@ -29,7 +29,11 @@ torch.jit.trace(model, x[:1]).save("traced_model.pt")
 '''
 
 
-@pytest.mark.parametrize("batch,dims", [(5, "20,33,17,10"), (1, "16,64,8")])
+FULL = "784,1000,1773,1773,1773,1773,1773,1124,1000"      # model.py:14-30, the 18.2 M-parameter ModulusLab MLP (configs 1 and 4)
+
+
+@pytest.mark.parametrize("batch,dims", [(5, "20,33,17,10"), (1, "16,64,8"), (256, FULL), (1, FULL)],
+                         ids=["toy-b5", "toy-b1", "model.py-b256", "model.py-b1"])
 def test_demo_out_identical_to_reference(tmp_path, batch, dims):
     import torch
     if not torch.cuda.is_available():
@@ -43,7 +47,7 @@ def test_demo_out_identical_to_reference(tmp_path, batch, dims):
     subprocess.check_call([sys.executable, "-c", GEN, "7", str(batch), dims], cwd=tmp_path)
     d_ref, d_our = tmp_path / "ref", tmp_path / "our"
     d_ref.mkdir(); d_our.mkdir()
-    r = subprocess.run([ref, "../traced_model.pt", "../sample_input.pt"], cwd=d_ref, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([ref, "../traced_model.pt", "../sample_input.pt"], cwd=d_ref, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stderr[-500:]
     env = dict(os.environ, ZKDL_SEED="1234", ZKDL_DUMP_PROOF="proof.txt")
     o = subprocess.run([ours, "../traced_model.pt", "../sample_input.pt"], cwd=d_our, capture_output=True, text=True, timeout=600, env=env)

@@ -119,20 +119,30 @@ __global__ void __launch_bounds__(THREADS) k_fr_fold_multi(const Fr* __restrict_
 // ------------------------------------------------------------------------------------------------ eq tables
 // E[i] = prod_j (bit_j(i) ? q[j] : 1 - q[j]), i < 2^t  (q[0] binds the least-significant index bit).
 // rev = 1 swaps the two factors (used for the generator weights of me_open).
-__global__ void __launch_bounds__(TAIL_THREADS) k_eq_small(const Fr* __restrict__ q, int t, int rev, Fr* __restrict__ E) {
-  // single CTA, levels 0..t-1, t <= 11 handled with TAIL_THREADS threads looping
-  if (threadIdx.x == 0) E[0] = Fr::one();
-  __syncthreads();
-  for (int j = 0; j < t; ++j) {
-    Fr qj = q[j];
-    size_t half = (size_t)1 << j;
-    for (size_t i = threadIdx.x; i < half; i += blockDim.x) {
-      Fr e = E[i];
-      Fr hi = mul(e, qj), lo = sub(e, hi);
-      if (rev) { E[i] = hi; E[i + half] = lo; } else { E[i] = lo; E[i + half] = hi; }
+// One CTA per table (blockIdx.x selects q + qoff[b], t[b], E[b]; up to two tables per launch).  eq over t <= 12 variables
+// factors into two half tables of <= 64 entries (<= 6 dependent products, built by the first 128 threads) and one
+// product per entry: no per-level barrier chain (the level-by-level doubling took 14 us per table, all of it latency).
+struct EqJob { const Fr* q; int t; Fr* E; };
+__global__ void __launch_bounds__(TAIL_THREADS) k_eq_small(EqJob j0, EqJob j1, int rev) {
+  __shared__ Fr half[2][64];
+  const EqJob j = blockIdx.x ? j1 : j0;
+  const int tl = j.t / 2, th = j.t - tl;
+  const int tid = threadIdx.x, which = tid >> 6, i = tid & 63;
+  if (which < 2) {
+    const int nb = which ? th : tl, base = which ? tl : 0;
+    if (i < (1 << nb)) {
+      Fr r = Fr::one();
+      for (int b = 0; b < nb; ++b) {
+        Fr qb = j.q[base + b];
+        bool bit = (i >> b) & 1;
+        r = mul(r, (bit != (rev != 0)) ? qb : sub(Fr::one(), qb));
+      }
+      half[which][i] = r;
     }
-    __syncthreads();
   }
+  __syncthreads();
+  const size_t n = (size_t)1 << j.t, mask = ((size_t)1 << tl) - 1;
+  for (size_t e = tid; e < n; e += blockDim.x) j.E[e] = mul(half[0][e & mask], half[1][e >> tl]);
 }
 
 // ------------------------------------------------------------------------------------------------ sumcheck rounds
@@ -304,15 +314,19 @@ __global__ void __launch_bounds__(THREADS) k_eq_outer(const Fr* __restrict__ lo,
 }
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st) {
   (void)q_host;
-  if (t <= 11) { ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, t, rev, E)); return ZK_OK; }
-  // eq(q, i) factors over the low tl and high t - tl variables: two small single-CTA tables + one product pass
-  // (3 launches instead of one per level).  Up to 22 variables both halves fit k_eq_small; beyond that recurse on hi.
-  int tl = 11, th = t - tl;
+  if (t <= 12) { EqJob j{q_dev, t, E}; ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(j, j, rev)); return ZK_OK; }
+  // eq(q, i) factors over the low tl and high t - tl variables: two small tables (one launch, one CTA each) + one product
+  // pass.  Up to 24 variables both halves fit k_eq_small; beyond that recurse on the high part.
+  int tl = 12, th = t - tl;
   Scratch lo, hi; int rc;
   if ((rc = lo.alloc(sizeof(Fr) * ((size_t)1 << tl), st))) return rc;
   if ((rc = hi.alloc(sizeof(Fr) * ((size_t)1 << th), st))) return rc;
-  ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(q_dev, tl, rev, lo.as<Fr>()));
-  if ((rc = build_eq_table(q_dev + tl, nullptr, th, rev, hi.as<Fr>(), st))) return rc;
+  EqJob jl{q_dev, tl, lo.as<Fr>()}, jh{q_dev + tl, th, hi.as<Fr>()};
+  if (th <= 12) ZK_LAUNCH(k_eq_small<<<2, TAIL_THREADS, 0, st>>>(jl, jh, rev));
+  else {
+    ZK_LAUNCH(k_eq_small<<<1, TAIL_THREADS, 0, st>>>(jl, jl, rev));
+    if ((rc = build_eq_table(q_dev + tl, nullptr, th, rev, hi.as<Fr>(), st))) return rc;
+  }
   size_t n = (size_t)1 << t;
   ZK_LAUNCH(k_eq_outer<<<stream_grid(n, THREADS), THREADS, 0, st>>>(lo.as<Fr>(), hi.as<Fr>(), tl, n, E));
   return ZK_OK;

@@ -268,6 +268,31 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t* __restrict__ offse
   }
 }
 
+// Few-keys path (openings, commitment-vector evaluations: at most SMALL_KEYS (row, bucket) keys): both exclusive scans
+// (bucket offsets, partial slots), the chunk plan and the per-key chunk counts in ONE single-CTA launch instead of eight.
+static constexpr uint32_t SMALL_KEYS = 16384;
+__global__ void __launch_bounds__(1024) k_msm_scan_small(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursors,
+                                                         uint32_t nkeys, uint32_t target, uint32_t* __restrict__ plan, uint32_t* __restrict__ pslot) {
+  const uint32_t per = (nkeys + blockDim.x - 1) / blockDim.x;
+  const uint32_t lo = threadIdx.x * per, hi = lo + per < nkeys ? lo + per : nkeys;
+  uint32_t s = 0, total;
+  for (uint32_t k = lo; k < hi; ++k) s += counts[k];
+  uint32_t off = block_exclusive_scan(s, &total);
+  for (uint32_t k = lo; k < hi; ++k) { offsets[k] = off; cursors[k] = off; off += counts[k]; }
+  uint32_t CH = (total + target - 1) / target; if (CH < 4) CH = 4;
+  if (threadIdx.x == 0) { offsets[nkeys] = total; plan[0] = CH; plan[1] = (total + CH - 1) / CH; }
+  __syncthreads();                                          // offsets[] of the neighbouring thread ranges
+  s = 0;
+  for (uint32_t k = lo; k < hi; ++k) { uint32_t b = offsets[k], e = offsets[k + 1]; s += b == e ? 0u : ((e - 1) / CH - b / CH + 1u); }
+  uint32_t ptotal;
+  off = block_exclusive_scan(s, &ptotal);
+  for (uint32_t k = lo; k < hi; ++k) {
+    uint32_t b = offsets[k], e = offsets[k + 1];
+    pslot[k] = off; off += b == e ? 0u : ((e - 1) / CH - b / CH + 1u);
+  }
+  if (threadIdx.x == 0) pslot[nkeys] = ptotal;
+}
+
 // ---- skew-robust bucket accumulation.  The sorted entry list is cut into chunks of CH consecutive entries, one per
 // thread, regardless of bucket boundaries, so every thread performs exactly CH mixed additions whatever the digit
 // distribution is (a 254-bit scalar leaves the top window with 2 bits of entropy: three buckets receive a third of
@@ -324,18 +349,33 @@ __global__ void __launch_bounds__(G1_THREADS, 3) k_msm_accumulate(const uint32_t
   }
   partials[pslot[key] + (t - offsets[key] / CH)] = acc;
 }
-// bucket[key] = sum of its partials.  Buckets with few partials: one lane each.  Buckets with many (the skewed ones)
-// are appended to a list and summed by one warp each in k_msm_combine_heavy (strided loads + shuffle tree).
+// bucket[key] = sum of its partials, G lanes per key (strided partial sums + a shuffle tree inside the G-lane segment):
+// G = 1 when there are many keys, G = 8 on the few-keys path, where every bucket holds dozens of partials.  Buckets with
+// more than COMBINE_LIGHT * G partials (the skewed ones) are appended to a list and summed by one warp each in
+// k_msm_combine_heavy (strided loads + shuffle tree).
 static constexpr uint32_t COMBINE_LIGHT = 6;
+template <int G>
 __global__ void __launch_bounds__(G1_THREADS) k_msm_combine(const G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pslot, size_t nkeys,
                                                             G1XYZZ* __restrict__ buckets, uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_count) {
-  size_t key = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (key >= nkeys) return;
-  uint32_t base = pslot[key], np = pslot[key + 1] - base;
-  if (np > COMBINE_LIGHT) { heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key; return; }
+  const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t key = gid / G; const uint32_t g = (uint32_t)(gid % G);
+  const bool valid = key < nkeys;
+  if (G == 1 && !valid) return;
+  uint32_t base = 0, np = 0;
+  if (valid) { base = pslot[key]; np = pslot[key + 1] - base; }
+  const bool heavy = np > COMBINE_LIGHT * G;
   G1XYZZ acc = xyzz_inf();
-  for (uint32_t i = 0; i < np; ++i) acc = xyzz_add(acc, partials[base + i]);
-  buckets[key] = acc;
+  if (!heavy) for (uint32_t i = g; i < np; i += G) acc = xyzz_add(acc, partials[base + i]);
+  if (G > 1) {
+#pragma unroll 1
+    for (int off = G / 2; off > 0; off >>= 1) {
+      G1XYZZ o = shfl_xyzz(acc, off);
+      if (g < (uint32_t)off) acc = xyzz_add(acc, o);
+    }
+  }
+  if (valid && g == 0) {
+    if (heavy) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)key; else buckets[key] = acc;
+  }
 }
 __global__ void __launch_bounds__(G1_THREADS) k_msm_combine_heavy(const G1XYZZ* __restrict__ partials, const uint32_t* __restrict__ pslot,
                                                                   G1XYZZ* __restrict__ buckets, const uint32_t* __restrict__ heavy_list,
@@ -392,6 +432,60 @@ __global__ void k_msm_reduce(const G1XYZZ* __restrict__ buckets, int K, int spli
   }
   G1XYZZ r = block_sum_xyzz(val, sm);
   if (t == 0) group_out[blockIdx.x] = r;
+}
+// Window groups with few buckets (K <= 1024; the fixed-base c = 8 path has K = 128): one CTA of T <= 128 threads per group,
+// L = K / T consecutive buckets per thread, everything else in registers: running sums (2L additions), inclusive suffix
+// scan of the thread sums by warp shuffles (5 steps) + one cross-warp step, then a shuffle tree.  With L = 1 the result
+// is simply the sum of all suffix sums: 16 dependent additions for 128 buckets (the previous shared-memory version
+// needed 36 for 2048 buckets at 8 per thread, on a CTA that saturated one SM).  T = 32 for many rows (throughput:
+// 21 warp-additions per row), T = 128 for few (latency).  FINAL (one group per row): writes the Jacobian result itself.
+template <bool FINAL>
+__global__ void __launch_bounds__(128) k_msm_reduce_scan(const G1XYZZ* __restrict__ buckets, int K, G1XYZZ* __restrict__ group_out, G1Jac* __restrict__ out) {
+  __shared__ G1XYZZ wt[4];
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = T >> 5;
+  const int L = K >= T ? K / T : 1;                           // K and T are powers of two
+  const int Tp = K / L;                                       // threads that own buckets (<= T)
+  const G1XYZZ* B = buckets + (size_t)blockIdx.x * K;
+  G1XYZZ E = xyzz_inf(), tot = xyzz_inf();                    // E: sum of the thread's buckets -> inclusive suffix sum over threads
+  if (t < Tp) {
+    if (L == 1) E = B[t];
+    else for (int b = t * L + L - 1; b >= t * L; --b) { E = xyzz_add(E, B[b]); tot = xyzz_add(tot, E); }
+  }
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) {
+    G1XYZZ o = shfl_xyzz(E, d);
+    if (lane + d < 32) E = xyzz_add(E, o);
+  }
+  if (nw > 1) {
+    if (lane == 0) wt[warp] = E;
+    __syncthreads();
+    G1XYZZ S = xyzz_inf();
+#pragma unroll 1
+    for (int w = nw - 1; w > warp; --w) S = xyzz_add(S, wt[w]);
+    E = xyzz_add(E, S);
+    __syncthreads();
+  }
+  // sum_b (b + 1) B_b = sum_t tot_t + L * sum_{t >= 1} E_t;  for L = 1 (tot_t = B_t) that is sum_{t >= 0} E_t
+  G1XYZZ val = E;
+  if (L > 1) {
+    val = tot;
+    if (t > 0 && t < Tp) {
+      for (int l = L; l > 1; l >>= 1) E = xyzz_dbl(E);
+      val = xyzz_add(tot, E);
+    }
+  }
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) {
+    G1XYZZ o = shfl_xyzz(val, off);
+    if (lane < off) val = xyzz_add(val, o);
+  }
+  if (nw > 1) {
+    if (lane == 0) wt[warp] = val;
+    __syncthreads();
+    if (t == 0)
+      for (int w = 1; w < nw; ++w) val = xyzz_add(val, wt[w]);
+  }
+  if (t == 0) { if (FINAL) out[blockIdx.x] = xyzz_to_jac(val); else group_out[blockIdx.x] = val; }
 }
 __global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int split, int c, G1Jac* __restrict__ out) {
   size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -460,7 +554,8 @@ namespace zk {
 
 static int pick_c(const zkdl_g1_table* t, size_t m) {
   if (const char* e = getenv("ZKDL_MSM_C")) { int c = atoi(e); if (c >= 4 && c <= 16) return c; }   // tuning knob
-  if (t->full) return m >= 64 ? 8 : 12;
+  if (t->full) return 8;      // 128 buckets per row: the bucket reduction is 16 dependent additions (12 -> 2048 buckets was the
+                              // longest kernel of an opening); ZKDL_MSM_C=12 restores the wide windows for A/B runs
   int lg = 0; while (((size_t)1 << (lg + 1)) <= t->n) ++lg;
   int c = lg - 5; if (c < 4) c = 4; if (c > 16) c = 16;
   return c;
@@ -518,16 +613,13 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
 
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * nkeys, st));
   unsigned dgrid = g1_grid(m * cfg.n, 256);
-  ZK_LAUNCH(k_msm_digits<false><<<dgrid, 256, 0, st>>>(scalars, cfg, counts.as<uint32_t>(), nullptr));
-  ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), nkeys, tiles.as<uint32_t>()));
-  ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(tiles.as<uint32_t>(), ntiles, total.as<uint32_t>()));
-  ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(offsets.as<uint32_t>(), cursors.as<uint32_t>(), nkeys, tiles.as<uint32_t>(), total.as<uint32_t>()));
-  ZK_LAUNCH(k_msm_digits<true><<<dgrid, 256, 0, st>>>(scalars, cfg, cursors.as<uint32_t>(), entries.as<uint32_t>()));
+  const bool few_keys = nkeys <= SMALL_KEYS;
   // chunked accumulation: about two resident waves of threads, each with the same number of mixed additions
   uint32_t target = (uint32_t)num_sms() * 384 * 2;
+  const int G = nkeys <= 8192 ? 8 : 1;                          // combine lanes per bucket
   Scratch plan, heavy;
   if ((rc = plan.alloc(sizeof(uint32_t) * 2, st))) return rc;
-  size_t max_heavy = (nkeys + (size_t)target + 2) / (COMBINE_LIGHT + 1) + 1;
+  size_t max_heavy = (nkeys + (size_t)target + 2) / (COMBINE_LIGHT * G + 1) + 1;
   if ((rc = heavy.alloc(sizeof(uint32_t) * (max_heavy + 1), st))) return rc;
   ZK_CUDA(cudaMemsetAsync(heavy.p, 0, sizeof(uint32_t), st));
   if ((rc = pcounts.alloc(sizeof(uint32_t) * nkeys, st))) return rc;
@@ -535,17 +627,44 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   if ((rc = ptiles.alloc(sizeof(uint32_t) * ntiles, st))) return rc;
   if ((rc = ptotal.alloc(sizeof(uint32_t), st))) return rc;
   if ((rc = partials.alloc(sizeof(G1XYZZ) * (nkeys + (size_t)target + 2), st))) return rc;
-  ZK_LAUNCH(k_msm_plan<<<1, 1, 0, st>>>(offsets.as<uint32_t>(), nkeys, target, plan.as<uint32_t>()));
-  ZK_LAUNCH(k_msm_chunk_counts<<<g1_grid(nkeys, 256), 256, 0, st>>>(offsets.as<uint32_t>(), nkeys, plan.as<uint32_t>(), pcounts.as<uint32_t>()));
-  ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(pcounts.as<uint32_t>(), pslot.as<uint32_t>(), nkeys, ptiles.as<uint32_t>()));
-  ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(ptiles.as<uint32_t>(), ntiles, ptotal.as<uint32_t>()));
-  ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(pslot.as<uint32_t>(), pcounts.as<uint32_t>(), nkeys, ptiles.as<uint32_t>(), ptotal.as<uint32_t>()));
+  ZK_LAUNCH(k_msm_digits<false><<<dgrid, 256, 0, st>>>(scalars, cfg, counts.as<uint32_t>(), nullptr));
+  if (few_keys) {
+    ZK_LAUNCH(k_msm_scan_small<<<1, 1024, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), cursors.as<uint32_t>(), (uint32_t)nkeys, target,
+                                                    plan.as<uint32_t>(), pslot.as<uint32_t>()));
+    ZK_LAUNCH(k_msm_digits<true><<<dgrid, 256, 0, st>>>(scalars, cfg, cursors.as<uint32_t>(), entries.as<uint32_t>()));
+  } else {
+    ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(counts.as<uint32_t>(), offsets.as<uint32_t>(), nkeys, tiles.as<uint32_t>()));
+    ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(tiles.as<uint32_t>(), ntiles, total.as<uint32_t>()));
+    ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(offsets.as<uint32_t>(), cursors.as<uint32_t>(), nkeys, tiles.as<uint32_t>(), total.as<uint32_t>()));
+    ZK_LAUNCH(k_msm_digits<true><<<dgrid, 256, 0, st>>>(scalars, cfg, cursors.as<uint32_t>(), entries.as<uint32_t>()));
+    ZK_LAUNCH(k_msm_plan<<<1, 1, 0, st>>>(offsets.as<uint32_t>(), nkeys, target, plan.as<uint32_t>()));
+    ZK_LAUNCH(k_msm_chunk_counts<<<g1_grid(nkeys, 256), 256, 0, st>>>(offsets.as<uint32_t>(), nkeys, plan.as<uint32_t>(), pcounts.as<uint32_t>()));
+    ZK_LAUNCH(k_scan_tiles<<<ntiles, SCAN_T, 0, st>>>(pcounts.as<uint32_t>(), pslot.as<uint32_t>(), nkeys, ptiles.as<uint32_t>()));
+    ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(ptiles.as<uint32_t>(), ntiles, ptotal.as<uint32_t>()));
+    ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(pslot.as<uint32_t>(), pcounts.as<uint32_t>(), nkeys, ptiles.as<uint32_t>(), ptotal.as<uint32_t>()));
+  }
   ZK_LAUNCH(k_msm_accumulate<<<div_up((size_t)target + 1, G1_THREADS), G1_THREADS, 0, st>>>(entries.as<uint32_t>(), offsets.as<uint32_t>(), pslot.as<uint32_t>(),
                                                                                               t->pts, partials.as<G1XYZZ>(), nkeys, plan.as<uint32_t>()));
   uint32_t* hcount = heavy.as<uint32_t>(); uint32_t* hlist = hcount + 1;
-  ZK_LAUNCH(k_msm_combine<<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
+  if (G == 8) ZK_LAUNCH(k_msm_combine<8><<<div_up(nkeys * 8, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
+  else ZK_LAUNCH(k_msm_combine<1><<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
   ZK_LAUNCH(k_msm_combine_heavy<<<div_up(max_heavy * 32, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), buckets.as<G1XYZZ>(), hlist, hcount));
-  // reduce: up to 256-thread CTAs, RL (8) buckets per thread, more only when 16 CTAs per group are not enough
+  const size_t ngroups = m * (size_t)cfg.NG;
+  if (cfg.K <= 1024) {
+    // few buckets per group: register/shuffle reduction, one CTA per group; 32 threads when rows are plentiful, 128 otherwise
+    int T = ngroups >= (size_t)num_sms() * 2 ? 32 : 128;
+    if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;
+    if (cfg.NG == 1) {
+      ZK_LAUNCH(k_msm_reduce_scan<true><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, nullptr, out));
+      return ZK_OK;
+    }
+    if ((rc = groups.alloc(sizeof(G1XYZZ) * ngroups, st))) return rc;
+    ZK_LAUNCH(k_msm_reduce_scan<false><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>(), nullptr));
+    ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, 1, cfg.c, out));
+    return ZK_OK;
+  }
+  // many buckets per group (plain Pippenger with wide windows): up to 256-thread CTAs, RL (8) buckets per thread, more only
+  // when 16 CTAs per group are not enough
   static const int RL = getenv("ZKDL_MSM_RED_L") ? atoi(getenv("ZKDL_MSM_RED_L")) : 8;      // tuning knobs (powers of two)
   static const int RT = getenv("ZKDL_MSM_RED_T") ? atoi(getenv("ZKDL_MSM_RED_T")) : 256;
   int T = cfg.K / RL; if (T < 32) T = 32; if (T > RT) T = RT; if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;

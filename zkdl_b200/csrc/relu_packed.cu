@@ -8,8 +8,12 @@
 //     With eq(u[j+1:], g) = eq_lo(j, group-in-element) * eq_hi(element), round j's three coefficients are
 //     sum_elem eq_hi[elem] * sum_groups LUT_j[group][bit pattern], i.e. table look-ups + additions and 7 products per
 //     ELEMENT for all three rounds together, instead of 6 products per CELL PAIR per round.
-//   * after three rounds each table entry is V3[byte]; the folded table a^(3) (1/8 of the cells) is materialised in the
-//     same pass and the generic single-pass rounds (fr_kernels.cu) take over.
+//   * after three rounds each table entry is V3[byte]: round 3 pairs two of them, i.e. its coefficients are a function
+//     of 16 bits (a 65536-entry look-up table in L2, pre-weighted by the in-element eq factor), and the table after
+//     round 3 is V4[16-bit half].  For mag_bin (32 cells) round 4 pairs the two halves of an element: 6 products per
+//     ELEMENT.  k_bin_r34 does these rounds straight from the packed words and writes the folded table with ONE entry
+//     per element (a^(5) for mag_bin, a^(4) for rem_bin); only then do the generic single-pass rounds (fr_kernels.cu)
+//     take over.  The tables a^(3), a^(4) (8 and 4 entries per element) are never materialised.
 //   * mag_bin.partial_me(u, 32) / rem_bin.partial_me(u, 16) (zkrelu.cu:92,94) are per-bit sums of eq(u, elem).
 // All values are the same field elements the reference computes, so the proof is bit-identical (tests/test_gpu_parity.py).
 #include <atomic>
@@ -35,7 +39,13 @@ template <int Q> struct PackLayout {
   static constexpr int OFF_L1 = OFF_E0 + N0;               // [N1][16][3]
   static constexpr int OFF_L2 = OFF_L1 + N1 * 16 * 3;      // [N2][256][3]
   static constexpr int OFF_V3 = OFF_L2 + N2 * 256 * 3;     // [256]
-  static constexpr int TOTAL = OFF_V3 + 256;
+  static constexpr int TOTAL = OFF_V3 + 256;               // shared-memory part (rounds 0..2)
+  // L2-resident part (rounds 3..4), after the shared part in the same buffer
+  static constexpr int NH = Q / 16;                         // 16-bit halves per element
+  static constexpr int OFF_L3 = TOTAL;                      // [NH][65536][3], pre-weighted by eq(u[4:LOGQ], half)
+  static constexpr int OFF_V4 = OFF_L3 + NH * 65536 * 3;    // [65536]
+  static constexpr int TOTAL_ALL = OFF_V4 + 65536;
+  static constexpr int ROUNDS = LOGQ;                       // packed rounds: all in-element variables
 };
 
 // unweighted Fr_bin_sc_step coefficients of a pair (proof.cu:152-163)
@@ -52,50 +62,66 @@ __device__ __forceinline__ Fr eq_point(const Fr* q, int t, unsigned idx) {
   return r;
 }
 
-// Builds the look-up tables of the three packed rounds from the challenges (single CTA).
+// Builds the look-up tables of the packed rounds from the challenges.  CTA 0: the shared-memory tables of rounds 0..2;
+// CTAs 1..256: 256 entries each of the round-3 tables (every CTA recomputes the 4 + 16 + 256 folded cell values).
 template <int Q>
 __global__ void __launch_bounds__(256) k_bin_luts(const Fr* __restrict__ u, const Fr* __restrict__ v, Fr* __restrict__ lut) {
   using PL = PackLayout<Q>;
-  __shared__ Fr V1[4], V2[16], e1[PL::N1], e2[PL::N2];
+  __shared__ Fr V1[4], V2[16], V3[256], e1[PL::N1], e2[PL::N2], e3[PL::NH];
   const int tid = threadIdx.x;
   if (tid < 4) {
     Fr x0 = (tid & 1) ? Fr::one() : Fr::zero(), x1 = (tid >> 1) ? Fr::one() : Fr::zero();
     V1[tid] = fold_pair(x0, x1, v[0]);
   }
-  if (tid < PL::N0) lut[PL::OFF_E0 + tid] = eq_point(u + 1, PL::LOGQ - 1, tid);
-  if (tid < PL::N1) e1[tid] = eq_point(u + 2, PL::LOGQ - 2, tid);
-  if (tid < PL::N2) e2[tid] = eq_point(u + 3, PL::LOGQ - 3, tid);
+  if (blockIdx.x == 0) {
+    if (tid < PL::N0) lut[PL::OFF_E0 + tid] = eq_point(u + 1, PL::LOGQ - 1, tid);
+    if (tid < PL::N1) e1[tid] = eq_point(u + 2, PL::LOGQ - 2, tid);
+    if (tid < PL::N2) e2[tid] = eq_point(u + 3, PL::LOGQ - 3, tid);
+  } else if (tid < PL::NH) e3[tid] = eq_point(u + 4, PL::LOGQ - 4, tid);
   __syncthreads();
   if (tid < 16) V2[tid] = fold_pair(V1[tid & 3], V1[tid >> 2], v[1]);
   __syncthreads();
-  // round 1 tables: pattern = nibble -> pair (V1[lo 2 bits], V1[hi 2 bits])
-  for (int i = tid; i < PL::N1 * 16; i += blockDim.x) {
-    int t = i / 16, nib = i % 16; Fr c[3];
-    bin_coeffs(V1[nib & 3], V1[nib >> 2], c);
-    for (int k = 0; k < 3; ++k) lut[PL::OFF_L1 + i * 3 + k] = mul(e1[t], c[k]);
+  {                                                       // V3[byte] = fold of (V2[lo nibble], V2[hi nibble]) with v[2]
+    Fr x0 = V2[tid & 15], x1 = V2[tid >> 4];
+    V3[tid] = fold_pair(x0, x1, v[2]);
   }
-  // round 2 tables: pattern = byte -> pair (V2[lo nibble], V2[hi nibble]);  V3[byte] = fold of that pair with v[2]
-  for (int byte = tid; byte < 256; byte += blockDim.x) {
-    Fr x0 = V2[byte & 15], x1 = V2[byte >> 4], c[3];
-    bin_coeffs(x0, x1, c);
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    // round 1 tables: pattern = nibble -> pair (V1[lo 2 bits], V1[hi 2 bits])
+    for (int i = tid; i < PL::N1 * 16; i += blockDim.x) {
+      int t = i / 16, nib = i % 16; Fr c[3];
+      bin_coeffs(V1[nib & 3], V1[nib >> 2], c);
+      for (int k = 0; k < 3; ++k) lut[PL::OFF_L1 + i * 3 + k] = mul(e1[t], c[k]);
+    }
+    // round 2 tables: pattern = byte -> pair (V2[lo nibble], V2[hi nibble])
+    Fr c[3];
+    bin_coeffs(V2[tid & 15], V2[tid >> 4], c);
     for (int t = 0; t < PL::N2; ++t)
-      for (int k = 0; k < 3; ++k) lut[PL::OFF_L2 + (t * 256 + byte) * 3 + k] = mul(e2[t], c[k]);
-    lut[PL::OFF_V3 + byte] = fold_pair(x0, x1, v[2]);
+      for (int k = 0; k < 3; ++k) lut[PL::OFF_L2 + (t * 256 + tid) * 3 + k] = mul(e2[t], c[k]);
+    lut[PL::OFF_V3 + tid] = V3[tid];
+    return;
   }
+  // round 3: pattern = 16 bits -> pair (V3[lo byte], V3[hi byte]); V4[pattern] = fold of that pair with v[3]
+  const int h = (blockIdx.x - 1) * 256 + tid;
+  Fr x0 = V3[h & 255], x1 = V3[h >> 8], c[3];
+  bin_coeffs(x0, x1, c);
+  for (int t = 0; t < PL::NH; ++t)
+    for (int k = 0; k < 3; ++k) lut[PL::OFF_L3 + ((size_t)t * 65536 + h) * 3 + k] = PL::NH == 1 ? c[k] : mul(e3[t], c[k]);
+  lut[PL::OFF_V4 + h] = fold_pair(x0, x1, v[3]);
 }
 
 extern __shared__ __align__(16) unsigned char pk_smem[];
 
-// One pass over the packed words: rounds 0, 1, 2 of the binary sumcheck + the folded table a^(3).
+// One pass over the packed words: rounds 0, 1, 2 of the binary sumcheck.
 // partials[blockIdx][7] = {S0, S1[3], S2[3]}
 template <int Q, class T>
 __global__ void __launch_bounds__(512) k_bin_packed3(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e_hi, const Fr* __restrict__ lut,
-                                                     Fr* __restrict__ a3, Fr* __restrict__ partials) {
+                                                     Fr* __restrict__ partials) {
   using PL = PackLayout<Q>;
   Fr* sm = reinterpret_cast<Fr*>(pk_smem);
-  for (int i = threadIdx.x; i < PL::TOTAL; i += blockDim.x) sm[i] = lut[i];
+  for (int i = threadIdx.x; i < PL::OFF_V3; i += blockDim.x) sm[i] = lut[i];
   __syncthreads();
-  const Fr* E0 = sm + PL::OFF_E0; const Fr* L1 = sm + PL::OFF_L1; const Fr* L2 = sm + PL::OFF_L2; const Fr* V3 = sm + PL::OFF_V3;
+  const Fr* E0 = sm + PL::OFF_E0; const Fr* L1 = sm + PL::OFF_L1; const Fr* L2 = sm + PL::OFF_L2;
   Fr acc[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) acc[k] = Fr::zero();
@@ -117,7 +143,6 @@ __global__ void __launch_bounds__(512) k_bin_packed3(const T* __restrict__ packe
       uint32_t byte = (w >> (8 * t)) & 255u;
       const Fr* e = L2 + (t * 256 + byte) * 3;
       s2[0] = add(s2[0], e[0]); s2[1] = add(s2[1], e[1]); s2[2] = add(s2[2], e[2]);
-      a3[i * PL::N2 + t] = V3[byte];
     }
     acc[0] = add(acc[0], mul(eh, s0));
 #pragma unroll
@@ -133,8 +158,52 @@ __global__ void __launch_bounds__(512) k_bin_packed3(const T* __restrict__ packe
 #pragma unroll
     for (int k = 0; k < 7; ++k) partials[blockIdx.x * 7 + k] = acc[k];
 }
-// proof[0..8] from the per-CTA partials: (0, -S0, S0), S1, S2
-__global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict__ partials, unsigned nparts, Fr* __restrict__ proof) {
+// Rounds 3 (and 4 for 32-cell elements) from the packed words + the folded table with one entry per element.
+// partials[blockIdx][3 * (ROUNDS - 3)] = {S3[3] (, S4[3])}
+__device__ __forceinline__ Fr ldg_fr(const Fr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldg(q), b = __ldg(q + 1);
+  Fr r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+template <int Q, class T>
+__global__ void __launch_bounds__(256, 2) k_bin_r34(const T* __restrict__ packed, size_t n, const Fr* __restrict__ e_hi, const Fr* __restrict__ lut, Fr v4,
+                                                 Fr* __restrict__ out, Fr* __restrict__ partials) {
+  using PL = PackLayout<Q>;
+  constexpr int NACC = 3 * (PL::ROUNDS - 3);
+  const Fr* L3 = lut + PL::OFF_L3; const Fr* V4 = lut + PL::OFF_V4;
+  Fr acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = Fr::zero();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w = packed[i];
+    Fr eh = e_hi[i];
+    const Fr* e = L3 + (size_t)(w & 0xffffu) * 3;
+    Fr s3[3] = {ldg_fr(e), ldg_fr(e + 1), ldg_fr(e + 2)};
+    Fr x0 = ldg_fr(V4 + (w & 0xffffu));
+    if (Q == 32) {
+      const Fr* e1 = L3 + ((size_t)65536 + (w >> 16)) * 3;
+      s3[0] = add(s3[0], ldg_fr(e1)); s3[1] = add(s3[1], ldg_fr(e1 + 1)); s3[2] = add(s3[2], ldg_fr(e1 + 2));
+      Fr x1 = ldg_fr(V4 + (w >> 16)), c[3];
+      out[i] = bin_pair(x0, x1, eh, v4, c);                // round 4: the element's two halves
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc[3 + k] = add(acc[3 + k], c[k]);
+    } else {
+      out[i] = x0;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] = add(acc[k], mul(eh, s3[k]));
+  }
+  __shared__ Fr red[3 * 32];
+  block_reduce_fr<3>(acc, red);
+  if (NACC > 3) { __syncthreads(); block_reduce_fr<3>(acc + (NACC > 3 ? 3 : 0), red); }
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) partials[blockIdx.x * NACC + k] = acc[k];
+}
+// proof[0 .. 3 * ROUNDS) from the per-CTA partials: (0, -S0, S0), S1, S2 from k_bin_packed3, then S3 (, S4) from k_bin_r34
+__global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict__ partials, unsigned nparts, const Fr* __restrict__ partials2, unsigned nparts2,
+                                                           int nacc2, Fr* __restrict__ proof) {
   __shared__ Fr red[3 * 32];
   Fr acc[7];
 #pragma unroll
@@ -151,6 +220,17 @@ __global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict_
     proof[0] = Fr::zero(); proof[1] = neg(acc[0]); proof[2] = acc[0];
     for (int k = 0; k < 6; ++k) proof[3 + k] = acc[1 + k];
   }
+  __syncthreads();
+  Fr b[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b[k] = Fr::zero();
+  for (unsigned i = threadIdx.x; i < nparts2; i += blockDim.x)
+    for (int k = 0; k < nacc2; ++k) b[k] = add(b[k], partials2[(size_t)i * nacc2 + k]);
+  block_reduce_fr<3>(b, red);
+  __syncthreads();
+  block_reduce_fr<3>(b + 3, red);
+  if (threadIdx.x == 0)
+    for (int k = 0; k < nacc2; ++k) proof[9 + k] = b[k];
 }
 
 // partial_me(u, Q) of a 0/1 table: out[bit] = sum over elements with that bit set of eq(u, elem).  Lane = bit.
@@ -214,20 +294,28 @@ static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkd
   if ((rc = vd.alloc(sizeof(Fr) * k, st))) return rc;
   ZK_CUDA(cudaMemcpyAsync(ud.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
   ZK_CUDA(cudaMemcpyAsync(vd.p, v_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
-  if ((rc = lut.alloc(sizeof(Fr) * PL::TOTAL, st))) return rc;
-  ZK_LAUNCH(k_bin_luts<Q><<<1, 256, 0, st>>>(ud.as<Fr>(), vd.as<Fr>(), lut.as<Fr>()));
+  if ((rc = lut.alloc(sizeof(Fr) * PL::TOTAL_ALL, st))) return rc;
+  ZK_LAUNCH(k_bin_luts<Q><<<257, 256, 0, st>>>(ud.as<Fr>(), vd.as<Fr>(), lut.as<Fr>()));
   if ((rc = ehi.alloc(sizeof(Fr) * n, st))) return rc;
   if ((rc = build_eq_table(ud.as<Fr>() + PL::LOGQ, u_host + PL::LOGQ, (int)L, 0, ehi.as<Fr>(), st))) return rc;
-  if ((rc = a3.alloc(sizeof(Fr) * n * PL::N2, st))) return rc;
-  unsigned grid = (unsigned)num_sms();                     // one CTA per SM (the look-up tables take 64-119 KB of shared memory)
+  if ((rc = a3.alloc(sizeof(Fr) * n, st))) return rc;      // the folded table after the packed rounds: one entry per element
+  unsigned grid = (unsigned)num_sms();                     // one CTA per SM (the look-up tables take 56-111 KB of shared memory)
   if ((size_t)grid * 512 > n) grid = div_up(n, 512);
   if ((rc = parts.alloc(sizeof(Fr) * 7 * grid, st))) return rc;
-  size_t smem = sizeof(Fr) * PL::TOTAL;
+  size_t smem = sizeof(Fr) * PL::OFF_V3;
   ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), a3.as<Fr>(), parts.as<Fr>()));
-  ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, proof_sc));
-  // rounds 3.. on the folded table: binary_sumcheck(a3, u[3:], v[3:]) has exactly the remaining rounds and the final a(0)
-  if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n * PL::N2, u_host + 3, v_host + 3, k - 3, reinterpret_cast<zkdl_fr_t*>(proof_sc + 9), st))) return rc;
+  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), parts.as<Fr>()));
+  constexpr int NACC = 3 * (PL::ROUNDS - 3);
+  unsigned grid2 = (unsigned)num_sms() * 4;
+  if ((size_t)grid2 * 256 > n) grid2 = div_up(n, 256);
+  Scratch parts2;
+  if ((rc = parts2.alloc(sizeof(Fr) * NACC * grid2, st))) return rc;
+  Fr v4; for (int i = 0; i < 8; ++i) v4.v[i] = v_host[4].val[i];
+  ZK_LAUNCH(k_bin_r34<Q, T><<<grid2, 256, 0, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), v4, a3.as<Fr>(), parts2.as<Fr>()));
+  ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, parts2.as<Fr>(), grid2, NACC, proof_sc));
+  // remaining rounds on the folded table: binary_sumcheck(a, u[R:], v[R:]) has exactly those rounds and the final a(0)
+  constexpr int R = PL::ROUNDS;
+  if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n, u_host + R, v_host + R, k - R, reinterpret_cast<zkdl_fr_t*>(proof_sc + 3 * R), st))) return rc;
   // partial_me(u_recover, Q)
   unsigned rgrid = (unsigned)num_sms() * 2;
   if ((size_t)rgrid * 8 * 4 > n) rgrid = div_up(n, 32);
