@@ -96,13 +96,12 @@ torch.jit.trace(model, x[:1]).save("traced_model.pt")
 
 def run_reference(args):
     """The reference's own implementation of the path is CUDA only (no CPU prover), rebuilt for sm_100 from
-    /root/reference by oracle/build_ref.sh.  Two modes, chosen so that the whole run ends within a few minutes:
-      * steps + warmup <= 4: every step is one run of the reference's own ./demo on the full 18.2 M-param model, batch 256,
-        timed by its own Timer (demo.cu:124-138) — 30-50 s of wall time per run (model load + its slow weight commitment);
-      * otherwise: every step is a BOUNDED SAMPLE, one hidden layer of that model (2048x2048 weights, batch 256:
-        zkReLU::prove + zkFC::prove through the reference's public API, oracle/ref_harness.cu `time layer`), ~1.5 s, scaled
-        to the 8-layer proof by layer counts/sizes.  The sample under-estimates the reference (its full demo runs slower
-        than the sum of its layers), i.e. it is conservative for the ratio."""
+    /root/reference by oracle/build_ref.sh.  Every invocation runs the STOCK path once: the reference's own ./demo on the
+    full 18.2 M-param model, batch 256, timed by its own Timer (demo.cu:124-138) — 30-50 s of wall time (model load + its
+    slow weight commitment); that run is `value`.  With steps + warmup <= 4 every step is such a run.  Otherwise the steps
+    are a BOUNDED SAMPLE reported beside it (`sample`): one hidden layer of that model (2048x2048 weights, batch 256:
+    zkReLU::prove + zkFC::prove through the reference's public API, oracle/ref_harness.cu `time layer`, ~1.5 s each), scaled
+    to the 8-layer proof by layer counts/sizes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -119,37 +118,35 @@ def run_reference(args):
     libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
     env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.environ.get("LD_LIBRARY_PATH", ""), CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
     sampler = ClockSampler(); sampler.start(); t_begin = time.time()
-    if args.steps + args.warmup <= 4:
-        tmp = tempfile.mkdtemp(prefix="zkdl_ref_")
-        subprocess.check_call([sys.executable, "-c", MODEL_GEN, str(BATCH)], cwd=tmp)
-        times = []
-        for it in range(args.warmup + args.steps):
-            out = subprocess.run([demo, "traced_model.pt", "sample_input.pt"], cwd=tmp, env=env, capture_output=True, text=True, timeout=1800)
-            m = re.search(r"Proof time: ([0-9.eE+-]+) seconds per data point", out.stdout)
-            if out.returncode != 0 or not m:
-                print(json.dumps({"impl": "reference", "unavailable": f"reference demo failed rc={out.returncode}: {(out.stderr or out.stdout)[-200:]!r}"}))
-                return
-            if it >= args.warmup:
-                times.append(float(m.group(1)) * BATCH)
-        val = sum(times) / len(times)
-        sample = ("full workload: the reference's own ./demo (oracle/_ref/demo, -arch=sm_100 -dlto) on the 18.2M-param model, batch 256, GPU 0, "
-                  "timed by its own Timer around demo.cu:124-138; one host thread")
-        extra = {}
-    else:
+    full_mode = args.steps + args.warmup <= 4
+    tmp = tempfile.mkdtemp(prefix="zkdl_ref_")
+    subprocess.check_call([sys.executable, "-c", MODEL_GEN, str(BATCH)], cwd=tmp)
+    times = []
+    for it in range(args.warmup + args.steps if full_mode else 1):
+        out = subprocess.run([demo, "traced_model.pt", "sample_input.pt"], cwd=tmp, env=env, capture_output=True, text=True, timeout=1800)
+        m = re.search(r"Proof time: ([0-9.eE+-]+) seconds per data point", out.stdout)
+        if out.returncode != 0 or not m:
+            print(json.dumps({"impl": "reference", "unavailable": f"reference demo failed rc={out.returncode}: {(out.stderr or out.stdout)[-200:]!r}"}))
+            return
+        if it >= args.warmup or not full_mode:
+            times.append(float(m.group(1)) * BATCH)
+    val = sum(times) / len(times)
+    sample = (f"full workload, stock path: the reference's own ./demo (oracle/_ref/demo, -arch=sm_100 -dlto) on the 18.2M-param model, batch 256, GPU 0, "
+              f"timed by its own Timer around demo.cu:124-138; one host thread; {len(times)} run(s) of 30-50 s wall each")
+    extra = {"full_demo_runs": len(times), "full_demo_s": times}
+    if not full_mode:
         n = args.warmup + args.steps
         out = subprocess.run([harness, "time", "layer", "11", str(n), str(BATCH)], env=env, capture_output=True, text=True, timeout=3600)
         rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{") and "layer_prove" in l]
-        if out.returncode != 0 or len(rows) < n:
-            print(json.dumps({"impl": "reference", "unavailable": f"ref_harness failed rc={out.returncode}: {(out.stderr or out.stdout)[-200:]!r}"}))
-            return
-        rows = rows[args.warmup:]
-        fc_s = sum(r["fc_seconds"] for r in rows) / len(rows); relu_s = sum(r["relu_seconds"] for r in rows) / len(rows)
-        # 8 zkFC proofs: 5 at 2048x2048 + three smaller (1024x1024, 1024x2048, 2048x1024 ~ 0.75 each); 7 zkReLU: 6 at 2^19 + one at 2^18
-        val = fc_s * 7.25 + relu_s * 6.5
-        sample = (f"bounded sample: one hidden layer (2048x2048 weights, batch 256) through the reference's public API on GPU 0 "
-                  f"(oracle/_ref/ref_harness time layer): zkFC::prove {fc_s:.3f}s x7.25 + zkReLU::prove {relu_s:.3f}s x6.5; the reference's full "
-                  f"./demo on the same box measures 15.7-29 s (profiles/r1_bench_reference_n1*.json)")
-        extra = {"sample_s_per_step": fc_s + relu_s}
+        if out.returncode == 0 and len(rows) >= n:
+            rows = rows[args.warmup:]
+            fc_s = sum(r["fc_seconds"] for r in rows) / len(rows); relu_s = sum(r["relu_seconds"] for r in rows) / len(rows)
+            # 8 zkFC proofs: 5 at 2048x2048 + three smaller (1024x1024, 1024x2048, 2048x1024 ~ 0.75 each); 7 zkReLU: 6 at 2^19 + one at 2^18
+            extra["sample"] = {"value_s": fc_s * 7.25 + relu_s * 6.5, "steps": len(rows), "s_per_step": fc_s + relu_s,
+                               "what": f"bounded sample beside the stock run: one hidden layer (2048x2048 weights, batch 256) through the reference's public API "
+                                       f"(oracle/_ref/ref_harness time layer): zkFC::prove {fc_s:.3f}s x7.25 + zkReLU::prove {relu_s:.3f}s x6.5"}
+        else:
+            extra["sample"] = {"unavailable": f"ref_harness failed rc={out.returncode}: {(out.stderr or out.stdout)[-200:]!r}"}
     clocks = sampler.stop(t_begin, time.time())
     base.update({"value": val, "ms_per_step": val * 1e3, "clocks": clocks, "gpu_launches": None,
                  "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,6 +201,33 @@ def cpu_baseline_sample():
                       f"{time.time() - t_all:.1f}s of CPU work, scaled to the 8-layer batch-256 proof by table sizes"}
 
 
+# measured ceilings of the integer pipe on this pool's B200 (tools/microbench.cu, profiles/r1_microbench_b200.jsonl)
+FR_MUL_CEIL_G, FQ_MUL_CEIL_G, IMAD_PEAK_T = 58.0, 30.2, 18.1        # G Fr products/s, G Fq products/s, T 32-bit IMAD/s
+FR_MACS, FQ_MACS = 136.0, 300.0                                      # 32x32->64 multiply-adds per Montgomery product (2N^2 + N)
+
+
+def kernel_rooflines(prof, hbm_peak):
+    """Per-kernel entries from the library's event profiler (zkdl_prof_dump) over whole proofs issued on ONE stream, so that
+    every bracketed kernel runs alone: share of the profiled kernel time, achieved algorithmic GB/s (SURVEY.md §8d's Fr-cell
+    model) against the HBM peak, achieved Montgomery products/s against the microbenchmark ceilings and against the nominal
+    18.1 T IMAD/s."""
+    tot = sum(v["ms"] for v in prof.values()) or 1.0
+    out = []
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        sec = v["ms"] * 1e-3
+        e = {"kernel": name, "launches": v["launches"], "ms_total": v["ms"], "us_per_launch": 1e3 * v["ms"] / max(v["launches"], 1), "share_of_profiled": v["ms"] / tot}
+        if v["bytes"] and sec:
+            e["hbm"] = {"achieved": v["bytes"] / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": v["bytes"] / sec / 1e9 / hbm_peak,
+                        "algorithmic_bytes_per_launch": v["bytes"] / v["launches"]}
+        muls, macs, ceil = (v["fq_mul"], FQ_MACS, FQ_MUL_CEIL_G) if v["fq_mul"] else (v["fr_mul"], FR_MACS, FR_MUL_CEIL_G)
+        if muls and sec:
+            e["imad"] = {"products_per_s_G": muls / sec / 1e9, "ceiling_G": ceil, "frac_of_microbench_ceiling": muls / sec / 1e9 / ceil,
+                         "imad_T_per_s": muls * macs / sec / 1e12, "peak_T": IMAD_PEAK_T, "frac_of_imad_peak": muls * macs / sec / 1e12 / IMAD_PEAK_T,
+                         "field": "Fq (381-bit)" if v["fq_mul"] else "Fr (255-bit)"}
+        out.append(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -229,46 +253,49 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     zk.lib()
 
-    dims = mlp.demo_layer_dims()
-    ws, x = mlp.synthetic_mlp(dims, BATCH, seed=0)
-    t0 = time.time()
-    P = mlp.MLPProver(ws, gen_seed=1)
-    torch.cuda.synchronize()
-    setup_s = time.time() - t0
-    x_host = x.cpu().pin_memory()
-    P.forward(x)
-    nl = len(P.layers)
-    # N > 1: the 37 independent pieces of the 15 layer proofs (zkFC = sumcheck + opening, zkReLU = 3 sumchecks) are
-    # spread over the ranks by a deterministic longest-first plan (parallel.partition_subtasks); no data-path collective.
-    plan = parallel.partition_subtasks([(L.I, L.O) for L in P.layers], P.B, world)[rank] if world > 1 else None
-    meta = {(k_, i): (L.I, L.ngens, P.B * L.O) for i, L in enumerate(P.layers) for k_ in ("fc", "relu")}
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms
+
+    dims = mlp.demo_layer_dims()
+    ws, x = mlp.synthetic_mlp(dims, BATCH, seed=0)
+    barrier()
+    t0 = time.time()
+    P = mlp.MLPProver(ws, gen_seed=1, world=world, rank=rank)      # N > 1: Commitment::commit sharded by row + all-gather
+    barrier()
+    setup_s = time.time() - t0
+    x_host = x.cpu().pin_memory()
+    P.forward(x)
+    P.check_range()
+    nl = len(P.layers)
+    # N > 1: the 37 independent pieces of the 15 layer proofs (zkFC = sumcheck + opening, zkReLU = 3 sumchecks) are
+    # spread over the ranks by a deterministic longest-first plan (parallel.partition_subtasks); no data-path collective.
+    plan = parallel.partition_subtasks([(L.I, L.O) for L in P.layers], P.B, world)[rank] if world > 1 else None
+    meta = {(k_, i): (L.I, L.ngens, P.B * L.O) for i, L in enumerate(P.layers) for k_ in ("fc", "relu")}
     proof_sizes = []
 
-    def prove_step(seed):
-        parts = P.prove(seed=seed, parts=plan)
+    def prove_step(seed, overlap_forward=False):
+        parts = P.prove(seed=seed, parts=plan, overlap_forward=overlap_forward)
         if world == 1:
             return torch.cat([t.reshape(-1) for p in parts for t in p[2:]])
         flat = parallel.pack_owned(parts, plan, meta)   # this rank's proof segments (parallel.assemble is the inverse)
-        if world > 1:                                   # proof elements of the other ranks' pieces -> rank 0
-            if not proof_sizes:                         # per-rank sizes depend only on the model shape: exchange once
-                szs = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-                dist.all_gather(szs, torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"))
-                proof_sizes.extend(int(s_.item()) for s_ in szs)
-            parts = parallel.gather_proof(flat, world, rank, "cuda", sizes=proof_sizes)
-            if rank == 0:
-                flat = torch.cat(parts)
-        return flat
+        if not proof_sizes:                             # per-rank sizes depend only on the model shape: exchange once
+            szs = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+            dist.all_gather(szs, torch.tensor([flat.numel()], dtype=torch.int64, device="cuda"))
+            proof_sizes.extend(int(s_.item()) for s_ in szs)
+        parts = parallel.gather_proof(flat, world, rank, "cuda", sizes=proof_sizes)   # proof elements of the other ranks' pieces -> rank 0
+        return torch.cat(parts) if rank == 0 else flat
 
     def e2e_step(seed):
         xd = x_host.cuda(non_blocking=True)             # H2D of this step's input batch from pinned memory
-        P.forward(xd)
-        flat = prove_step(seed)
+        P.forward(xd)                                   # quantised forward pass; every layer records an event ...
+        flat = prove_step(seed, overlap_forward=True)   # ... and each piece waits only for its own layer's tables
         return flat.cpu()                               # D2H of the proof elements
 
     for w in range(max(args.warmup, 3)):
@@ -288,9 +315,7 @@ def main():
     barrier()
     t_end = time.time()
     launches = zk.launch_count() - l0
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     if args.skip_extras:
@@ -309,18 +334,11 @@ def main():
     for k in range(args.steps):
         pr = e2e_step(4000 + k)
     e1.record(); barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    P.check_range()
     h2d = x_host.numel() * 4
     d2h = pr.numel() * 4
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant HBM kernel + the two other BASELINE metrics (rank 0, N = 1 workload sizes)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,7 +346,66 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     extra = {}
-    # fold kernel on the FC4096 weight table (config 2): 2^24 Fr = 512 MiB > L2, three variables per launch
+
+    # ---- N > 1: the two north_star splits on their own workloads (every rank takes part; timed as the max over ranks)
+    if world > 1:
+        reps = 3
+        lgN = 24
+        lo, hi = parallel.shard_range(1 << lgN, world, rank)
+        rng = np.random.default_rng(100 + rank)
+        ks = rng.integers(0, 1 << 32, size=(hi - lo, 8), dtype=np.uint64).astype(np.uint32); ks[:, 7] %= 1944954707
+        G = zk.g1_mul(zk.to_device(mlp._generator()), zk.to_device(ks))
+        tab = zk.G1Table(G, full=False); del G
+        sc = rng.integers(0, 1 << 32, size=(hi - lo, 8), dtype=np.uint64).astype(np.uint32); sc[:, 7] %= 1944954707
+        sc = zk.to_device(sc)
+        fn = lambda: parallel.msm_sharded(lambda: zk.msm(tab, sc, 1, False), zk.g1_sum, None, world)
+        fn(); barrier(); e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); barrier()
+        t_msm = max_over_ranks(e0.elapsed_time(e1) / reps)
+        tab.close(); del sc
+        extra["msm_by_point_range"] = {"log_n": lgN, "ms": t_msm, "Mpts_per_s": (1 << lgN) / t_msm / 1e3,
+                                       "what": "one 2^24-point 255-bit MSM, N/P contiguous (base, scalar) pairs per rank, all-gather of P partial points + local G1 sum"}
+        k = 26
+        lo, hi = parallel.shard_range(1 << k, world, rank)
+        g = torch.Generator(device="cuda").manual_seed(11 + rank)
+        a = torch.randint(-(2 ** 31), 2 ** 31 - 1, (hi - lo, 8), dtype=torch.int32, device="cuda", generator=g); a[:, 7] &= 0x3FFFFFFF
+        u, v = zk.random_vec(1, k), zk.random_vec(2, k)
+        ops = parallel.CapiOps()
+
+        def all_gather(t_):
+            outs = [torch.empty_like(t_) for _ in range(world)]
+            dist.all_gather(outs, t_.contiguous())
+            return outs
+        fn = lambda: parallel.sumcheck_sharded("bin", ops, [a], u, v, world, rank, all_gather)
+        fn(); barrier(); e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); barrier()
+        t_sc = max_over_ranks(e0.elapsed_time(e1) / reps)
+        del a
+        extra["sumcheck_by_leading_variables"] = {"log_n": k, "kind": "binary", "ms": t_sc, "algorithmic_GBps": 96.0 * (1 << k) / t_sc / 1e6,
+                                                  "what": "binary sumcheck of a 2^26-entry (2 GiB) Fr table, rank r holds the slice with leading bits r; "
+                                                          "one all-gather of the 3 k_local + 1 coefficients per rank"}
+        extra["commit_sharded_by_row_setup_s"] = setup_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel rooflines: two whole proofs issued on ONE stream with the library's event profiler on
+    P.prove(seed=5000, streams=1)
+    zk.prof_enable(True)
+    for k in range(2):
+        P.prove(seed=5001 + k, streams=1)
+    prof = zk.prof_dump()
+    zk.prof_enable(False)
+    kernels = kernel_rooflines(prof, hbm_peak)
+    dominant = kernels[0] if kernels else None
+
+    # ---- roofline of the HBM-side metric (M3): fold kernel on the FC4096 weight table (config 2): 2^24 Fr = 512 MiB > L2
     n = 1 << 24
     Wbig = torch.randint(-(2 ** 31), 2 ** 31 - 1, (n, 8), dtype=torch.int32, device="cuda"); Wbig[:, 7] &= 0x3FFFFFFF
     u3 = zk.random_vec(77, 3)
@@ -347,48 +424,94 @@ def main():
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": 597113856.0,   # dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1_kernels_full_summary.json
                 "algorithmic_bytes_per_launch": alg_bytes, "actual_min_bytes_per_launch": 32.0 * n * (1 + 1 / 8), "ms_per_launch": fold_ms,
-                "peak_source": peak_src, "note": "denominator is SURVEY §8d's per-round Fr-cell model; the kernel folds 3 rounds per pass so "
-                                                 "its real DRAM traffic is 36 n B (= measured traffic, no re-reads). ncu: DRAM 24% of peak, "
-                                                 "sm__throughput 83%: the kernel is IMAD-bound (7 Montgomery products per 8 elements at the "
-                                                 "measured 58 G Fr-mul/s ceiling), see profiles/README.md"}
+                "peak_source": peak_src, "note": "BASELINE metric M3 (sumcheck fold HBM GB/s); denominator is SURVEY §8d's per-round Fr-cell model; the kernel "
+                                                 "folds 3 rounds per pass so its real DRAM traffic is 36 n B (= measured traffic, no re-reads). ncu: DRAM 24% of "
+                                                 "peak, sm__throughput 83%: the kernel is IMAD-bound (7 Montgomery products per 8 elements at the measured "
+                                                 "58 G Fr-mul/s ceiling). This kernel is ~1% of the proving step: the step's dominant kernels are in "
+                                                 "`roofline_dominant` / `roofline_kernels`"}
     extra["fold_hbm_gbs_algorithmic"] = achieved
     extra["fold_hbm_gbs_actual_traffic"] = 36.0 * n / (fold_ms * 1e-3) / 1e9
     del Wbig
-    # MSM: fixed-base (window tables) commitment MSM, m = 1, N = 2^16 full-width scalars + the 2^22-cell demo commit
-    N = 1 << 16
-    ks = zk.to_device(zk.random_vec(5, N))
-    G = zk.g1_mul(zk.to_device(mlp._generator()), ks)
-    for full, key in ((True, "msm_mpts_s_fixed_base_2^16"), (False, "msm_mpts_s_plain_2^16")):
-        tab = zk.G1Table(G, full=full)
-        sc = zk.to_device(zk.random_vec(6, N))
-        for _ in range(2):
-            zk.msm(tab, sc, 1, False)
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize(); e0.record()
-        for _ in range(5):
-            zk.msm(tab, sc, 1, False)
+        for _ in range(reps):
+            fn()
         e1.record(); torch.cuda.synchronize()
-        extra[key] = N / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e6
-        tab.close()
+        return e0.elapsed_time(e1) / reps
+
+    if world == 1:
+        # ---- config 2: the FC4096 zkFC sumcheck set (X.partial_me, W.partial_me, inner-product sumcheck, Z(u))
+        I = O = 4096
+        g = torch.Generator(device="cuda").manual_seed(3)
+
+        def small_fr(cnt, bits):
+            v = torch.randint(-(1 << (bits - 1)), 1 << (bits - 1), (cnt, 1), generator=g, device="cuda", dtype=torch.int32).float() / 65536.0
+            q = zk.float_to_fr(v, cnt, 1)
+            return zk.fr_elementwise(zk.OP_MONT, q, out=q)
+        W4, X4 = small_fr(I * O, 16), small_fr(BATCH * I, 16)
+        Z4 = zk.fr_matmul(X4, W4, BATCH, I, O)
+        u_bs, u_in, u_out = zk.random_vec(3, 8), zk.random_vec(4, 12), zk.random_vec(5, 12)
+
+        def sc_set():
+            Xr = zk.fr_partial_me(X4, u_bs, I); Wr = zk.fr_partial_me(W4, u_out, 1)
+            zk.ip_sumcheck(Xr, Wr, u_in); zk.fr_me(Z4, np.concatenate([u_out, u_bs]))
+        t_sc = timed(sc_set)
+        alg = 96.0 * (I * O) * (1 - 2.0 ** -12) + 96.0 * (BATCH * I) * (1 - 2.0 ** -8) + 96.0 * (BATCH * O) * (1 - 2.0 ** -20)
+        extra["fc4096_sumcheck_set"] = {"ms": t_sc, "algorithmic_GB": alg / 1e9, "algorithmic_GBps": alg / t_sc / 1e6, "frac_of_hbm_peak": alg / t_sc / 1e6 / hbm_peak,
+                                        "what": "config 2: 4096x4096 16-bit weights, batch 256: X.partial_me + W.partial_me + inner_product_sumcheck + Z(u)"}
+        del W4, X4, Z4
+        # ---- config 3: G1 MSM sweep, plain Pippenger (no precomputed tables), m = 1; 255-bit and 16-bit signed scalars
+        sweep = {}
+        gen = zk.to_device(mlp._generator())
+        for lg in (16, 18, 20, 22, 24):
+            N = 1 << lg
+            rng = np.random.default_rng(lg)
+            ks = rng.integers(0, 1 << 32, size=(N, 8), dtype=np.uint64).astype(np.uint32); ks[:, 7] %= 1944954707
+            G = zk.g1_mul(gen, zk.to_device(ks))
+            tab = zk.G1Table(G, full=False); del G
+            sc = rng.integers(0, 1 << 32, size=(N, 8), dtype=np.uint64).astype(np.uint32); sc[:, 7] %= 1944954707
+            sc = zk.to_device(sc)
+            small = torch.zeros((N, 8), dtype=torch.int32, device="cuda")
+            small[:, 0] = torch.randint(0, 1 << 15, (N,), dtype=torch.int32, device="cuda")
+            r_ = 3 if lg >= 22 else 5
+            t_full = timed(lambda: zk.msm(tab, sc, 1, False), reps=r_, warm=1)
+            t_small = timed(lambda: zk.msm(tab, small, 1, False), reps=r_, warm=1)
+            sweep[f"2^{lg}"] = {"ms_255bit": t_full, "Mpts_per_s_255bit": N / t_full / 1e3, "ms_16bit": t_small, "Mpts_per_s_16bit": N / t_small / 1e3}
+            if lg == 16:
+                tabf = zk.G1Table(zk.g1_mul(gen, zk.to_device(ks)), full=True)
+                t_fb = timed(lambda: zk.msm(tabf, sc, 1, False))
+                sweep["2^16"]["ms_255bit_fixed_base"] = t_fb; sweep["2^16"]["Mpts_per_s_255bit_fixed_base"] = N / t_fb / 1e3
+                tabf.close()
+            tab.close(); del sc, small
+        extra["msm_sweep"] = sweep
+        extra["msm_mpts_s_plain_2^16"] = sweep["2^16"]["Mpts_per_s_255bit"]
+        extra["msm_mpts_s_fixed_base_2^16"] = sweep["2^16"]["Mpts_per_s_255bit_fixed_base"]
+        extra["msm_mpts_s_plain_2^24"] = sweep["2^24"]["Mpts_per_s_255bit"]
     L2 = P.layers[2]
-    torch.cuda.synchronize(); e0.record()
-    for _ in range(3):
-        zk.commit(L2.gens, L2.W)
-    e1.record(); torch.cuda.synchronize()
-    extra["commit_2048x2048_ms"] = e0.elapsed_time(e1) / 3
+    extra["commit_2048x2048_ms"] = timed(lambda: zk.commit(L2.gens, L2.W), reps=3, warm=1)
     extra["commit_msm_mpts_s"] = (L2.I * L2.O) / (extra["commit_2048x2048_ms"] * 1e-3) / 1e6
     extra["setup_s"] = setup_s
+    extra["forward_ms"] = timed(lambda: P.forward(x), reps=5, warm=1)
 
     cpu = None if (args.skip_cpu_baseline or world > 1) else cpu_baseline_sample()      # host baseline: rank 0 at N=1 only
     line = {"metric": METRIC, "value": ms / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32 limbs (Fr 255-bit / Fq 381-bit modular)", "data": "synthetic",
             "config": {"workload": "demo MLP 784-1000-1773x5-1124-1000 (18.2M params), batch 256, 8 zkFC + 7 zkReLU proofs",
-                       "batch": BATCH, "parallelism": f"layer proofs split into 37 independent pieces over {world} ranks" if world > 1 else "single GPU",
+                       "batch": BATCH, "parallelism": f"layer proofs split into 37 independent pieces over {world} ranks; commit sharded by row" if world > 1 else "single GPU",
                        "l2": "working set (>5 GB of Fr tables) exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_ms / 1e3, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "input batch H2D + quantised forward pass + proof + proof D2H (the reference's timed region excludes the forward pass)"},
-            "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
+                    "note": "input batch H2D + quantised forward pass + proof + proof D2H (the reference's timed region excludes the forward pass); "
+                            "each piece starts as soon as its own layer's forward tables are ready"},
+            "roofline": roofline, "roofline_dominant": dominant, "roofline_kernels": kernels[:12],
+            "roofline_kernels_note": "chosen by the event profiler, not by hand: two whole proofs issued on one stream (every kernel runs alone), CUDA events around "
+                                     "each launch on its stream; `share_of_profiled` is of the bracketed kernels' total. IMAD-bound kernels: Montgomery products/s "
+                                     "against tools/microbench.cu's ceilings (58 G Fr/s, 30.2 G Fq/s) and against the nominal 18.1 T IMAD/s; HBM: SURVEY §8d bytes",
+            "cpu_baseline": cpu, "extra": extra}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

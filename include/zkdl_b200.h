@@ -37,6 +37,12 @@ int zkdl_version(void);
 int zkdl_scratch_reserve(size_t bytes, void* stream);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t zkdl_launch_count(void);
+/* Per-kernel profiler for bench.py's roofline entries (no reference counterpart; the reference times with Timer around
+ * whole operators, timer.cpp).  zkdl_prof_enable(1) clears the records and makes every hot-kernel launch record CUDA events
+ * on its own stream; zkdl_prof_dump synchronises the device and writes one text line per kernel
+ * "name launches total_ms algorithmic_bytes fr_products fq_products" into buf (returns the size needed). */
+int zkdl_prof_enable(int on);
+size_t zkdl_prof_dump(char* buf, size_t cap);
 
 /* ------------------------------------------------------------------ Fr tensors (fr-tensor.cu) */
 enum { ZKDL_OP_ADD = 0, ZKDL_OP_SUB = 1, ZKDL_OP_MUL = 2, ZKDL_OP_NEG = 3, ZKDL_OP_MONT = 4, ZKDL_OP_UNMONT = 5 };

@@ -252,3 +252,39 @@ def test_subtask_gather_assemble_world2_gloo():
     for p in procs:
         p.join(120); assert p.exitcode == 0
     assert all(ok for _, ok in items)
+
+
+# ------------------------------------------------------------------------------------------------ commit sharded by row
+def _commit_worker(rank, world, port, q):
+    """Commitment::commit by row ranges (SURVEY.md §8e row 1) with the CPU oracle as the local committer, default
+    torch.distributed all-gather (gloo), m = 5 rows over 2 ranks (uneven shards: 3 + 2, padded gather)."""
+    import numpy as np
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(9)
+    ng, m = 4, 5
+    G = orc.g1_mul(orc.g1_generator(), orc.to_limbs([int(v) for v in rng.integers(1, 1 << 60, size=ng)]), fast=True)
+    W = orc.fr_from_ints([int(v) for v in rng.integers(-3000, 3000, size=ng * m)], mont=True)
+
+    def commit(gens, t):                         # torch int32 limbs in/out, like capi.commit
+        out = orc.commit(gens, t.numpy().view(np.uint32), fast=True)
+        return torch.from_numpy(np.ascontiguousarray(out).view(np.int32)).reshape(-1, 36)
+
+    Wt = torch.from_numpy(W.view(np.int32))
+    got = parallel.commit_sharded(commit, G, Wt, ng, world, rank).numpy().view(np.uint32)
+    full = orc.commit(G, W, fast=True)
+    q.put((rank, got.shape[0] == m and bool(orc.g1_eq(got, full).all())))
+    dist.destroy_process_group()
+
+
+def test_commit_sharded_world2_gloo_matches_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 32500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_commit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs: p.start()
+    items = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(120); assert p.exitcode == 0
+    assert all(ok for _, ok in items), items

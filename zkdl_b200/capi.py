@@ -446,6 +446,24 @@ def scratch_reserve(nbytes):
     _check(lib().zkdl_scratch_reserve(_sz(nbytes), _stream()))
 
 
+def prof_enable(on=True):
+    """Per-kernel profiler of the library (zkdl_prof_enable): clears the records and switches event bracketing on/off."""
+    _check(lib().zkdl_prof_enable(int(bool(on))))
+
+
+def prof_dump():
+    """{kernel: {"launches", "ms", "bytes", "fr_mul", "fq_mul"}} since the last prof_enable (synchronises the device)."""
+    lib().zkdl_prof_dump.restype = C.c_size_t
+    need = lib().zkdl_prof_dump(None, _sz(0))
+    buf = C.create_string_buffer(int(need) + 16)
+    lib().zkdl_prof_dump(buf, _sz(len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        f = line.rsplit(" ", 5)
+        out[f[0]] = {"launches": int(float(f[1])), "ms": float(f[2]), "bytes": float(f[3]), "fr_mul": float(f[4]), "fq_mul": float(f[5])}
+    return out
+
+
 def random_vec(seed, n):
     import numpy as np
     out = np.zeros((n, 8), np.uint32)

@@ -3,6 +3,7 @@
 #include <string.h>
 #include <atomic>
 #include <map>
+#include <string>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -12,6 +13,29 @@ namespace zk {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_prof_on{0};
+
+namespace {
+struct ProfRec { const char* what; cudaEvent_t e0, e1; double bytes, fr_mul, fq_mul; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+int prof_pre(const char* what, cudaStream_t st, double bytes, double fr_mul, double fq_mul) {
+  ProfRec r{what, nullptr, nullptr, bytes, fr_mul, fq_mul};
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_post(int idx, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx >= 0 && idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, st);
+}
+void prof_set_fq_mul(int idx, double fq_mul) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (idx >= 0 && idx < (int)g_prof.size()) g_prof[idx].fq_mul = fq_mul;
+}
 
 void set_last_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
@@ -117,6 +141,36 @@ int zkdl_scratch_reserve(size_t bytes, void* stream) {
     if (!rc) rc = ss.join(st);
   }
   return rc;
+}
+int zkdl_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(zk::g_prof_mu);
+  for (auto& r : zk::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  zk::g_prof.clear();
+  zk::g_prof_on.store(on ? 1 : 0);
+  return ZKDL_OK;
+}
+size_t zkdl_prof_dump(char* buf, size_t cap) {
+  // one line per kernel: name launches total_ms bytes fr_mul fq_mul   (the device must be idle: events are synchronised)
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(zk::g_prof_mu);
+  struct Agg { double n = 0, ms = 0, bytes = 0, fr = 0, fq = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : zk::g_prof) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) continue;
+    std::string name(r.what);
+    size_t cut = name.find("<<<"); if (cut != std::string::npos) name.resize(cut);
+    std::string clean; for (char c : name) if (c != ' ') clean += c;
+    Agg& a = agg[clean]; a.n += 1; a.ms += ms; a.bytes += r.bytes; a.fr += r.fr_mul; a.fq += r.fq_mul;
+  }
+  std::string out;
+  for (auto& kv : agg) {
+    char line[512];
+    snprintf(line, sizeof(line), "%s %.0f %.6f %.0f %.0f %.0f\n", kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.fr, kv.second.fq);
+    out += line;
+  }
+  if (buf && cap) { size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
+  return out.size() + 1;
 }
 const char* zkdl_last_error(void) { return zk::g_err; }
 int zkdl_version(void) { return 100; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include "field.cuh"
 
 namespace zk {
@@ -46,6 +47,29 @@ struct SideStream {
   int join(cudaStream_t main);
 };
 SideStream& side_stream(int idx);          // idx < 4
+
+// ---- launch accounting and the optional per-kernel profiler (zkdl_prof_enable / zkdl_prof_dump, common.cu): with the
+// profiler on, ZK_LAUNCH_P brackets the launch with CUDA events on ITS stream and files the elapsed time under the kernel's
+// name together with the launch's algorithmic work (bytes by SURVEY.md §8d's model, Fr / Fq Montgomery products).
+extern std::atomic<uint64_t> g_launches;
+extern std::atomic<int> g_prof_on;
+int prof_pre(const char* what, cudaStream_t st, double bytes, double fr_mul, double fq_mul);
+void prof_post(int idx, cudaStream_t st);
+void prof_set_fq_mul(int idx, double fq_mul);
+#define ZK_LAUNCH(...)            \
+  do {                            \
+    __VA_ARGS__;                  \
+    zk::g_launches.fetch_add(1);  \
+    ZK_CHECK_LAUNCH();            \
+  } while (0)
+#define ZK_LAUNCH_P(st_, bytes_, fr_, fq_, ...)                                                                          \
+  do {                                                                                                                   \
+    int pi__ = zk::g_prof_on.load(std::memory_order_relaxed) ? zk::prof_pre(#__VA_ARGS__, st_, bytes_, fr_, fq_) : -1;   \
+    __VA_ARGS__;                                                                                                         \
+    zk::g_launches.fetch_add(1);                                                                                         \
+    if (pi__ >= 0) zk::prof_post(pi__, st_);                                                                             \
+    ZK_CHECK_LAUNCH();                                                                                                   \
+  } while (0)
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 int num_sms();

@@ -17,13 +17,6 @@
 #include "../../include/zkdl_b200.h"
 
 namespace zk {
-extern std::atomic<uint64_t> g_launches;
-#define ZK_LAUNCH(...)            \
-  do {                            \
-    __VA_ARGS__;                  \
-    zk::g_launches.fetch_add(1);  \
-    ZK_CHECK_LAUNCH();            \
-  } while (0)
 
 static constexpr int THREADS = 256;
 static constexpr size_t TAIL_N = 2048;        // tables this small finish in one single-CTA launch
@@ -359,7 +352,8 @@ static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k,
     static const int fold_cap = getenv("ZKDL_FOLD_CAP") ? atoi(getenv("ZKDL_FOLD_CAP")) : 16;
     size_t blocks = (total + fold_block - 1) / fold_block, capb = (size_t)num_sms() * fold_cap;
     unsigned grid = (unsigned)(blocks < capb ? (blocks ? blocks : 1) : capb);
-    if (R == 3) ZK_LAUNCH(k_fr_fold_multi<3><<<grid, fold_block, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
+    // 48 n B per round, R rounds fused = 96 n (1 - 2^-R) B algorithmic (real traffic: 32 n (1 + 2^-R)); 2^R - 1 products per output
+    if (R == 3) ZK_LAUNCH_P(st, 96.0 * cur_n * (1.0 - 0.125), 7.0 * total, 0.0, k_fr_fold_multi<3><<<grid, fold_block, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     else if (R == 2) ZK_LAUNCH(k_fr_fold_multi<2><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     else ZK_LAUNCH(k_fr_fold_multi<1><<<grid, THREADS, 0, st>>>(cur, dst, xs.as<Fr>() + j, cur_n, out_rows, w));
     cur = dst; cur_n = total; rows = out_rows; which ^= 1; j += R;
@@ -411,13 +405,16 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
     bool fold_e = (KIND != SC_IP) && esize >= 2;
     size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
     unsigned grid = stream_grid(H, THREADS);
-    ZK_LAUNCH(k_sc_round<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
-                                                         host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j));
+    // 48 n B per table per round (+ the eq table: 32 B read per two pairs, 16 B written); 5 / 7 / 6 products per pair
+    const double tables = KIND == SC_BIN ? 1.0 : 2.0, mulpp = KIND == SC_IP ? 5.0 : (KIND == SC_HP ? 7.0 : 6.0);
+    ZK_LAUNCH_P(st, 48.0 * cur_n * tables + (KIND != SC_IP ? 24.0 * esize : 0.0), mulpp * out_size, 0.0,
+                k_sc_round<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
+                                                           host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j));
     ca = abuf[which]; cb = bbuf[which]; which ^= 1; cur_n = out_size;
     if (fold_e) { ewhich ^= 1; esize /= 2; }
   }
   if (j < k) {
-    ZK_LAUNCH(k_sc_tail<KIND><<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(ca), abuf[which], const_cast<Fr*>(cb), bbuf[which], ebuf[ewhich], ebuf[ewhich ^ 1],
+    ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_sc_tail<KIND><<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(ca), abuf[which], const_cast<Fr*>(cb), bbuf[which], ebuf[ewhich], ebuf[ewhich ^ 1],
                                                           xs.as<Fr>() + j, (int)(k - j), cur_n, esize, proof + 3 * j));
   } else {
     ZK_CUDA(cudaMemcpyAsync(proof + 3 * k, ca, sizeof(Fr), cudaMemcpyDeviceToDevice, st));

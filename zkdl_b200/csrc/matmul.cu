@@ -24,13 +24,6 @@ struct zkdl_mm_weights {
 };
 
 namespace zk {
-extern std::atomic<uint64_t> g_launches;
-#define ZK_LAUNCH(...)            \
-  do {                            \
-    __VA_ARGS__;                  \
-    zk::g_launches.fetch_add(1);  \
-    ZK_CHECK_LAUNCH();            \
-  } while (0)
 
 static constexpr int THREADS = 256;
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }

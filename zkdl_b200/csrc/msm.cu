@@ -22,13 +22,6 @@
 #include "../../include/zkdl_b200.h"
 
 namespace zk {
-extern std::atomic<uint64_t> g_launches;
-#define ZK_LAUNCH(...)            \
-  do {                            \
-    __VA_ARGS__;                  \
-    zk::g_launches.fetch_add(1);  \
-    ZK_CHECK_LAUNCH();            \
-  } while (0)
 
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
 int fr_partial_me_dev(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t w, Fr* out, cudaStream_t st);
@@ -643,23 +636,31 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
     ZK_LAUNCH(k_scan_sums<<<1, SCAN_T, 0, st>>>(ptiles.as<uint32_t>(), ntiles, ptotal.as<uint32_t>()));
     ZK_LAUNCH(k_scan_apply<<<g1_grid(nkeys + 1, 256), 256, 0, st>>>(pslot.as<uint32_t>(), pcounts.as<uint32_t>(), nkeys, ptiles.as<uint32_t>(), ptotal.as<uint32_t>()));
   }
+  if (g_prof_on.load(std::memory_order_relaxed)) {          // profiling pass only: the real entry count (one synchronous 4-byte read)
+    uint32_t nent = 0;
+    ZK_CUDA(cudaMemcpyAsync(&nent, offsets.as<uint32_t>() + nkeys, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    ZK_CUDA(cudaStreamSynchronize(st));
+    // one mixed addition (madd-2008-s) = 8M + 2S = 10 Fq products per sorted entry
+    ZK_LAUNCH_P(st, 0.0, 0.0, 10.0 * nent, k_msm_accumulate<<<div_up((size_t)target + 1, G1_THREADS), G1_THREADS, 0, st>>>(
+        entries.as<uint32_t>(), offsets.as<uint32_t>(), pslot.as<uint32_t>(), t->pts, partials.as<G1XYZZ>(), nkeys, plan.as<uint32_t>()));
+  } else
   ZK_LAUNCH(k_msm_accumulate<<<div_up((size_t)target + 1, G1_THREADS), G1_THREADS, 0, st>>>(entries.as<uint32_t>(), offsets.as<uint32_t>(), pslot.as<uint32_t>(),
                                                                                               t->pts, partials.as<G1XYZZ>(), nkeys, plan.as<uint32_t>()));
   uint32_t* hcount = heavy.as<uint32_t>(); uint32_t* hlist = hcount + 1;
-  if (G == 8) ZK_LAUNCH(k_msm_combine<8><<<div_up(nkeys * 8, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
-  else ZK_LAUNCH(k_msm_combine<1><<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
-  ZK_LAUNCH(k_msm_combine_heavy<<<div_up(max_heavy * 32, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), buckets.as<G1XYZZ>(), hlist, hcount));
+  if (G == 8) ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_combine<8><<<div_up(nkeys * 8, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
+  else ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_combine<1><<<div_up(nkeys, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), nkeys, buckets.as<G1XYZZ>(), hlist, hcount));
+  ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_combine_heavy<<<div_up(max_heavy * 32, G1_THREADS), G1_THREADS, 0, st>>>(partials.as<G1XYZZ>(), pslot.as<uint32_t>(), buckets.as<G1XYZZ>(), hlist, hcount));
   const size_t ngroups = m * (size_t)cfg.NG;
   if (cfg.K <= 1024) {
     // few buckets per group: register/shuffle reduction, one CTA per group; 32 threads when rows are plentiful, 128 otherwise
     int T = ngroups >= (size_t)num_sms() * 2 ? 32 : 128;
     if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;
     if (cfg.NG == 1) {
-      ZK_LAUNCH(k_msm_reduce_scan<true><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, nullptr, out));
+      ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce_scan<true><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, nullptr, out));
       return ZK_OK;
     }
     if ((rc = groups.alloc(sizeof(G1XYZZ) * ngroups, st))) return rc;
-    ZK_LAUNCH(k_msm_reduce_scan<false><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>(), nullptr));
+    ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce_scan<false><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>(), nullptr));
     ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, 1, cfg.c, out));
     return ZK_OK;
   }
@@ -670,7 +671,7 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   int T = cfg.K / RL; if (T < 32) T = 32; if (T > RT) T = RT; if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;
   int split = cfg.K / (T * RL); if (split < 1) split = 1; if (split > 16) split = 16;
   if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG * split, st))) return rc;
-  ZK_LAUNCH(k_msm_reduce<<<(unsigned)(m * cfg.NG * split), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, split, groups.as<G1XYZZ>()));
+  ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce<<<(unsigned)(m * cfg.NG * split), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, split, groups.as<G1XYZZ>()));
   ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, split, cfg.c, out));
   return ZK_OK;
 }

@@ -22,13 +22,6 @@
 #include "../../include/zkdl_b200.h"
 
 namespace zk {
-extern std::atomic<uint64_t> g_launches;
-#define ZK_LAUNCH(...)            \
-  do {                            \
-    __VA_ARGS__;                  \
-    zk::g_launches.fetch_add(1);  \
-    ZK_CHECK_LAUNCH();            \
-  } while (0)
 
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
 
@@ -304,14 +297,17 @@ static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkd
   if ((rc = parts.alloc(sizeof(Fr) * 7 * grid, st))) return rc;
   size_t smem = sizeof(Fr) * PL::OFF_V3;
   ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ZK_LAUNCH(k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), parts.as<Fr>()));
+  // rounds 0..2 over Q n cells of 32 B by SURVEY.md §8d's Fr-cell model: 96 Q n (1 - 1/8) B; real traffic (sizeof(T) + 32) n B; 7 products per element
+  ZK_LAUNCH_P(st, 96.0 * Q * n * 0.875, 7.0 * n, 0.0, k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), parts.as<Fr>()));
   constexpr int NACC = 3 * (PL::ROUNDS - 3);
   unsigned grid2 = (unsigned)num_sms() * 4;
   if ((size_t)grid2 * 256 > n) grid2 = div_up(n, 256);
   Scratch parts2;
   if ((rc = parts2.alloc(sizeof(Fr) * NACC * grid2, st))) return rc;
   Fr v4; for (int i = 0; i < 8; ++i) v4.v[i] = v_host[4].val[i];
-  ZK_LAUNCH(k_bin_r34<Q, T><<<grid2, 256, 0, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), v4, a3.as<Fr>(), parts2.as<Fr>()));
+  // rounds 3 (and 4): tables of Q n / 8 (and Q n / 16) cells in the Fr-cell model; 3 (+ 6) products per element
+  ZK_LAUNCH_P(st, 48.0 * (Q * n / 8) * (Q == 32 ? 1.5 : 1.0), (Q == 32 ? 9.0 : 3.0) * n, 0.0,
+              k_bin_r34<Q, T><<<grid2, 256, 0, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), v4, a3.as<Fr>(), parts2.as<Fr>()));
   ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, parts2.as<Fr>(), grid2, NACC, proof_sc));
   // remaining rounds on the folded table: binary_sumcheck(a, u[R:], v[R:]) has exactly those rounds and the final a(0)
   constexpr int R = PL::ROUNDS;

@@ -29,8 +29,12 @@ class Layer:
 class MLPProver:
     """weights: list of float32 CUDA tensors shaped [in, out] (== nn.Linear.weight.t(), demo.cu:72)."""
 
-    def __init__(self, weights, gen_seed=1):
+    def __init__(self, weights, gen_seed=1, world=1, rank=0, all_gather=None):
+        """world > 1: Commitment::commit is sharded by row over the ranks (SURVEY.md §8e row 1, commitment.cu:29-41): rank r
+        commits rows [r m/P, (r+1) m/P) of every weight table and the row commitments are all-gathered
+        (parallel.commit_sharded); generators and window tables are replicated (|G| <= 4096 points)."""
         import torch
+        from . import parallel
         self.layers = []
         rng = np.random.default_rng(gen_seed)
         gen = zk.to_device(_generator())
@@ -45,7 +49,7 @@ class MLPProver:
             L.gens = zk.G1Table(L.G, full=True)
             q = zk.float_to_fr(w.contiguous(), L.I, L.O)                                     # zkfc.cu:90-100
             L.W = zk.fr_elementwise(zk.OP_MONT, q, out=q)
-            L.com = zk.commit(L.gens, L.W)                                                   # zkfc.cu:102
+            L.com = parallel.commit_sharded(zk.commit, L.gens, L.W, L.ngens, world, rank, all_gather)   # zkfc.cu:102
             L.com_table = zk.G1Table(L.com, full=True)
             L.mm = zk.MatmulWeights(L.W, L.I, L.O)                                           # integer copy for the forward product
             self.layers.append(L)
@@ -58,19 +62,29 @@ class MLPProver:
         L0 = self.layers[0]
         X = zk.float_to_fr(x.contiguous(), B, L0.I)                                          # zkfc.cu:106-115
         self.X = zk.fr_elementwise(zk.OP_MONT, X, out=X)                                     # demo.cu:119
+        import torch
         self.B = B
-        self.Z, self.A, self.aux = [], [], []
+        self.Z, self.A, self.aux, self.bad, self.ready = [], [], [], [], []
         cur = self.X
         for i, L in enumerate(self.layers):
             z = zk.fr_matmul_prepared(cur, L.mm, B)
             self.Z.append(z)
             if i + 1 < len(self.layers):
                 a, sign, mag, rem, bad = zk.relu_packed(z)                                  # aux kept bit-packed
-                self.A.append(a); self.aux.append((sign, mag, rem))
+                self.A.append(a); self.aux.append((sign, mag, rem)); self.bad.append(bad)
                 cur = a
+            ev = torch.cuda.Event(); ev.record()                                            # layer i's tables are final here
+            self.ready.append(ev)
         return self.Z[-1]
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None, parts=None):
+    def check_range(self):
+        """Activations outside +-2^47 are undefined in the reference (relu_kernel, zkrelu.cu:16-28); here they are
+        counted on the device.  Synchronises; raises if the last forward pass saw any."""
+        import torch
+        if self.bad and int(torch.stack(self.bad).sum().item()) != 0:
+            raise ValueError("zkReLU input outside +-2^47: the decomposition (and the reference's) is undefined for it")
+
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None, parts=None, overlap_forward=False):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
         fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); `parts` = {("fc"|"relu", layer):
         part mask} restricts it further to independent parts of a layer's proof (parallel.partition_subtasks): the
@@ -80,7 +94,9 @@ class MLPProver:
         proofs are issued on `streams` CUDA streams: the latency-bound bucket reductions of one layer's opening overlap
         the bandwidth-bound sumcheck passes of another.  With threads=True each stream is fed by its own host thread
         (ctypes releases the GIL, the library is thread-safe), so the ~1200 kernel launches of a proof are issued in
-        parallel instead of from one core."""
+        parallel instead of from one core.
+        overlap_forward: the pieces are issued in ascending layer order and each waits only for ITS layer's event of the
+        last forward() call, so proving the first layers overlaps the rest of the forward pass (the end-to-end path)."""
         import os
         import torch
         if threads is None:                              # ZKDL_PROVE_THREADS=0: issue from the calling thread (NVTX-scoped profiling)
@@ -159,15 +175,23 @@ class MLPProver:
             for f in [self._pools[s_].submit(reserve, s_) for s_ in range(old, streams)]:
                 f.result()
             torch.cuda.synchronize()
-        start = torch.cuda.Event(); start.record(main)
+        start = torch.cuda.Event()
+        order = list(range(len(tasks)))
+        if overlap_forward:
+            order.sort(key=lambda j: (tasks[j][1], tasks[j][0] != "fc"))      # fc i needs Z_i only; relu i also its aux tables
+        else:
+            start.record(main)
 
         def worker(slot):
             torch.cuda.set_device(dev)
             st = self._streams[slot]
-            st.wait_event(start)
+            if not overlap_forward:
+                st.wait_event(start)
             res = []
             with torch.cuda.stream(st):
-                for j in range(slot, len(tasks), streams):
+                for j in order[slot::streams]:
+                    if overlap_forward:
+                        st.wait_event(self.ready[tasks[j][1]])
                     res.append((j, run(tasks[j])))
             ev = torch.cuda.Event(); ev.record(st)
             return res, ev

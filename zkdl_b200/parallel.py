@@ -135,6 +135,25 @@ def gather_proof(flat, world, rank, device, sizes=None):
     return [o[:s] for o, s in zip(outs, sizes)]
 
 
+def commit_sharded(commit, gens, W, ngens, world, rank, all_gather=None):
+    """Commitment::commit partitioned by row (SURVEY.md §8e row 1; /root/reference/commitment.cu:29-41): the m = |W| / |G| rows
+    are independent commitments, so rank r computes rows [lo, hi) = shard_range(m, world, r) with the replicated generators
+    and the row commitments (144 B each) are all-gathered; no reduction.  commit(gens, t) -> [rows, 36] Jacobian limbs.
+    all_gather(x) -> list of every rank's x (default: torch.distributed.all_gather, padded to the largest shard)."""
+    if world == 1:
+        return commit(gens, W)
+    m = W.shape[0] // ngens
+    lo, hi = shard_range(m, world, rank)
+    part = commit(gens, W[lo * ngens: hi * ngens]) if hi > lo else W.new_zeros((0, 36))
+    if all_gather is not None:
+        return torch.cat(list(all_gather(part)))
+    mx = -(-m // world)
+    buf = part if part.shape[0] == mx else torch.cat([part, part.new_zeros((mx - part.shape[0], 36))])
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf.contiguous())
+    return torch.cat([o[: shard_range(m, world, r)[1] - shard_range(m, world, r)[0]] for r, o in enumerate(outs)])
+
+
 def shard_range(n, world, rank):
     """Contiguous point range [lo, hi) of rank `rank` for an MSM over n (base, scalar) pairs."""
     base, rem = divmod(n, world)
