@@ -318,6 +318,13 @@ int main(int argc, char** argv) {
       full_fc(out, 1u << k, 1u << k, B, false, 16);
     } else if (what == "msm") {         // full msm <log_n> 0 <out.bin>: config 3, (G * s).sum()
       full_msm(out, atoi(argv[3]));
+    } else if (what == "split") {       // full split <log_n> <window> <out.bin>: FrTensor::split on a ragged table (fr-tensor.cu:376-397)
+      uint n = (1u << atoi(argv[3])) + 5;
+      FrTensor a = rand_signed(n, 20, 4);
+      for (uint w : {(uint)atoi(argv[4]), 1u, 7u, n - 1}) {
+        auto pr = a.split(w);
+        out["split." + std::to_string(w) + ".first"] = fr_out(pr.first); out["split." + std::to_string(w) + ".second"] = fr_out(pr.second);
+      }
     } else { fprintf(stderr, "unknown full case\n"); return 1; }
     out["cuda_status"] = std::vector<uint32_t>(1, (uint32_t)cudaGetLastError());
     write_box(argv[5], out);

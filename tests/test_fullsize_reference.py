@@ -193,3 +193,9 @@ def test_msm_against_reference(zk, tmp_path, k):
         assert orc.g1_eq(zk.to_host(zk.msm(tab, s, 1, False)), ref["msm.full"].reshape(-1, 36)).all()
         tab.close()
     compare_boxes(ref, run_harness(TWIN, tmp_path, "twin", "msm", k, 0))
+
+
+def test_split_against_reference(zk, tmp_path):
+    """FrTensor::split (fr-tensor.cu:376-397) of the drop-in shim (two strided 2-D copies + ragged tail) on a ragged table,
+    windows 64 / 1 / 7 / n-1, against the reference's kernel."""
+    compare_boxes(run_harness(REF, tmp_path, "ref", "split", 12, 64), run_harness(TWIN, tmp_path, "twin", "split", 12, 64))

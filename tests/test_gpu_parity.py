@@ -129,7 +129,8 @@ def test_quantise_matmul_relu(zk):
     assert eq(zk.to_host(Z), oZ) and eq(zk.to_host(sign), osign) and eq(zk.to_host(mag), omag) and eq(zk.to_host(rem), orem)
 
 
-@pytest.mark.parametrize("case", ["tc_small", "tc_boundary", "a_too_big", "w_too_big", "generic_fr", "ragged_shape", "tc_long_k"])
+@pytest.mark.parametrize("case", ["tc_small", "tc_boundary", "a_too_big", "w_too_big", "generic_fr", "ragged_shape", "tc_long_k",
+                                  "umma_boundary", "umma_a_too_big", "umma_tiles"])
 def test_matmul_prepared_routes(zk, case):
     """zkdl_fr_matmul_prepared: the int8 tensor-core route, the int32 SIMT route and the generic Fr route agree with the
     oracle's Fr matmul bit for bit; the route is picked on the device from the operands' magnitudes."""
@@ -138,8 +139,10 @@ def test_matmul_prepared_routes(zk, case):
         M, K, N = 24, 40, 33
     if case == "tc_long_k":
         M, K, N = 128, 2048, 128
+    if case.startswith("umma"):                       # shapes the tcgen05 kernel takes (M % 128 == 0, N % 64 == 0, K % 128 == 0)
+        M, K, N = (256, 384, 192) if case == "umma_tiles" else (128, 256, 192)
     amax, wmax = (1 << 23) - 1, (1 << 15) - 1
-    if case in ("tc_small", "ragged_shape", "tc_long_k"):
+    if case in ("tc_small", "ragged_shape", "tc_long_k", "umma_tiles"):
         a = [int(v) for v in rng.integers(-(1 << 20), 1 << 20, size=M * K)]
         w = [int(v) for v in rng.integers(-(1 << 12), 1 << 12, size=K * N)]
     elif case == "generic_fr":
@@ -147,7 +150,7 @@ def test_matmul_prepared_routes(zk, case):
     else:
         a = [(amax, -amax, 0, 1, -1, 255, -256, 65535, -65536)[i % 9] for i in range(M * K)]
         w = [(wmax, -wmax, 0, 1, -1, 255, -256, 128, -129)[(5 * i + 2) % 9] for i in range(K * N)]
-        if case == "a_too_big":
+        if case in ("a_too_big", "umma_a_too_big"):
             a[7] = 1 << 23
         if case == "w_too_big":
             w[11] = -(1 << 15)

@@ -48,6 +48,16 @@ def test_corrupted_files_are_rejected(proof_path, tmp_path):
     t = copy.deepcopy(tasks); t[1]["fr"][-1, 0] ^= 1; rejected(public, t)                    # final value of the Hadamard sumcheck
     p = copy.deepcopy(public); p["layers"][3]["commitment"][0] = public["layers"][3]["commitment"][1]; rejected(p, tasks)
     p = copy.deepcopy(public); p["layers"][2]["generators"][5] = public["layers"][2]["generators"][6]; rejected(p, tasks)
+    # structure: a file with a layer proof missing, duplicated or reordered, or with challenge vectors whose
+    # lengths do not follow from the public shapes, must not pass
+    rejected(public, tasks[:-1])
+    rejected(public, tasks[1:])
+    rejected(public, tasks + [tasks[-1]])
+    rejected(public, [tasks[1], tasks[0]] + tasks[2:])
+    rejected(public, [])
+    t = copy.deepcopy(tasks); t[0]["challenges"][1] = t[0]["challenges"][1][:-1]; rejected(public, t)
+    t = copy.deepcopy(tasks); t[1]["challenges"][4] = np.concatenate([t[1]["challenges"][4], t[1]["challenges"][4][:1]]); rejected(public, t)
+    t = copy.deepcopy(tasks); t[1]["fr"] = t[1]["fr"][:-1]; rejected(public, t)
     bad.write_bytes(blob[: len(blob) // 2])
     with pytest.raises(ValueError):
         proof_file.verify_file(str(bad))

@@ -47,6 +47,15 @@ struct SideStream {
   int join(cudaStream_t main);
 };
 SideStream& side_stream(int idx);          // idx < 4
+// fork() now, join() on every way out of the scope: an early error return must not leave the side stream still reading
+// the caller's buffers while the caller frees them
+struct ForkScope {
+  SideStream& ss; cudaStream_t main; bool open = false;
+  ForkScope(SideStream& s, cudaStream_t m) : ss(s), main(m) {}
+  int fork() { int rc = ss.fork(main); open = rc == 0; return rc; }
+  int join() { if (!open) return 0; open = false; return ss.join(main); }
+  ~ForkScope() { if (open) ss.join(main); }
+};
 
 // ---- launch accounting and the optional per-kernel profiler (zkdl_prof_enable / zkdl_prof_dump, common.cu): with the
 // profiler on, ZK_LAUNCH_P brackets the launch with CUDA events on ITS stream and files the elapsed time under the kernel's

@@ -24,6 +24,8 @@ struct zkdl_mm_weights {
 };
 
 namespace zk {
+bool umma_matmul_shape_ok(size_t M, size_t K, size_t N);
+int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, size_t K, size_t N, const uint32_t* info, cudaStream_t st);
 
 static constexpr int THREADS = 256;
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -377,8 +379,11 @@ static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr*
     if ((rc = ap.alloc(TC_A_PLANES * rowsA * colsA, st))) return rc;
     ZK_LAUNCH(k_fr_to_i32<TC_A_PLANES><<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(A, ai.as<int32_t>(), rowsA * colsA, inf, inf + 1, ap.as<uint8_t>()));
     ZK_LAUNCH(k_mm_route<<<1, 1, 0, st>>>(inf, 1));
-    dim3 tgrid(div_up(colsB, TC_N), div_up(rowsA, TC_M));
-    ZK_LAUNCH(k_tc_matmul<<<tgrid, 256, 0, st>>>(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf));
+    // tcgen05 / TMEM / TMA kernel (matmul_umma.cu) when the shape tiles by 128 x 64 x 128, else the mma.sync kernel
+    if (!umma_matmul_shape_ok(rowsA, colsA, colsB) || umma_matmul_launch(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf, st) != ZK_OK) {
+      dim3 tgrid(div_up(colsB, TC_N), div_up(rowsA, TC_M));
+      ZK_LAUNCH(k_tc_matmul<<<tgrid, 256, 0, st>>>(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf));
+    }
   } else {
     ZK_LAUNCH(k_fr_to_i32<0><<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(A, ai.as<int32_t>(), rowsA * colsA, inf, inf + 1, nullptr));
   }

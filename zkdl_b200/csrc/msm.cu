@@ -707,7 +707,8 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   // latency-bound bucket reduction overlaps the opening MSM (joined before returning).
   SideStream& ss = side_stream(0);
   Scratch uq, E, tf; int rc;
-  if ((rc = ss.fork(st))) return rc;
+  ForkScope fs(ss, st);
+  if ((rc = fs.fork())) return rc;
   cudaStream_t side = ss.stream;
   {
     Scratch uqs, Es;
@@ -727,7 +728,7 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   else rc = fr_partial_me_dev(t, nt, u_hi, khi, w, tf.as<Fr>(), st);
   if (rc) return rc;
   rc = me_open_run(gens, tf.as<Fr>(), tf_n, u_host, klo, proof, ret, st);
-  int rj = ss.join(st);
+  int rj = fs.join();
   return rc ? rc : rj;
 }
 

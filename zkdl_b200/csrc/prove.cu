@@ -44,7 +44,8 @@ int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_mm_
   int rc;
   // The matmul sumcheck and the commitment opening are independent: the sumcheck part runs on a side stream.
   SideStream& ss = side_stream(1);
-  if ((rc = ss.fork(st))) return rc;
+  ForkScope fs(ss, st);
+  if ((rc = fs.fork())) return rc;
   void* sst = reinterpret_cast<void*>(ss.stream);
   size_t nip = 3 * ki + 2;
   if (parts & ZKDL_FC_SUMCHECK) {
@@ -74,7 +75,7 @@ int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_mm_
                   reinterpret_cast<G1Jac*>(proof_g1 + 1), reinterpret_cast<Fr*>(proof_fr + nip + 1), st);
     if (rc) return rc;
   }
-  return ss.join(st);
+  return fs.join();
 }
 
 size_t zkdl_zkrelu_proof_size(size_t n) {

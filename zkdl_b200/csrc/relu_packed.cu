@@ -359,16 +359,17 @@ int zkdl_zkrelu_prove_packed_parts(const zkdl_fr_t* X, const zkdl_fr_t* sign, co
   Fr* p_rem_rec = p;                      p += 16;
   // the three sumchecks are independent: mag_bin on the caller's stream, rem_bin and the Hadamard product on side streams
   SideStream& s1 = side_stream(1); SideStream& s2 = side_stream(2);
-  if ((rc = s1.fork(st))) return rc;
-  if ((rc = s2.fork(st))) return rc;
+  ForkScope f1(s1, st), f2(s2, st);
+  if ((rc = f1.fork())) return rc;
+  if ((rc = f2.fork())) return rc;
   if ((parts & ZKDL_RELU_MAG) &&
       (rc = packed_bin_and_recover<32, uint32_t>(mag_packed, n, L, u_z_host, v_z_host, erec.as<Fr>(), p_mag_sc, p_mag_rec, st))) return rc;
   if ((parts & ZKDL_RELU_REM) &&
       (rc = packed_bin_and_recover<16, uint16_t>(rem_packed, n, L, u_r_host, v_r_host, erec.as<Fr>(), p_rem_sc, p_rem_rec, s1.stream))) return rc;
   if ((parts & ZKDL_RELU_HP) &&
       (rc = zkdl_hp_sumcheck(X, sign, n, u_hp_host, v_hp_host, L, reinterpret_cast<zkdl_fr_t*>(p), reinterpret_cast<void*>(s2.stream)))) return rc;   // zkrelu.cu:99
-  if ((rc = s1.join(st))) return rc;
-  return s2.join(st);
+  if ((rc = f1.join())) return rc;
+  return f2.join();
 }
 
 }  // extern "C"

@@ -131,12 +131,21 @@ std::pair<FrTensor, FrTensor> FrTensor::split(uint window_size) const {         
   cuda_check(cudaMemsetAsync(out.first.gpu_data, 0, sizeof(Fr_t) * out_size, cur_stream()));
   cuda_check(cudaMemsetAsync(out.second.gpu_data, 0, sizeof(Fr_t) * out_size, cur_stream()));
   sync();
-  for (uint wid = 0; (size_t)wid * window_size < out_size; ++wid) {                // window-wise device copies
-    size_t dst = (size_t)wid * window_size, n0 = std::min<size_t>(window_size, out_size - dst);
-    size_t s0 = 2 * (size_t)wid * window_size, s1 = s0 + window_size;
-    if (s0 < size) copy(out.first.gpu_data + dst, gpu_data + s0, sizeof(Fr_t) * std::min<size_t>(n0, size - s0), cudaMemcpyDeviceToDevice);
-    if (s1 < size) copy(out.second.gpu_data + dst, gpu_data + s1, sizeof(Fr_t) * std::min<size_t>(n0, size - s1), cudaMemcpyDeviceToDevice);
+  // even windows -> first, odd windows -> second: two strided 2-D copies for the whole windows (source pitch 2 w, destination
+  // pitch w), then at most two ragged windows each by plain copies (the reference uses one kernel, fr-tensor.cu:376-397)
+  const size_t w = window_size, full_dst = out_size / w;
+  size_t full0 = size >= w ? (size - w) / (2 * w) + 1 : 0, full1 = size / (2 * w);
+  if (full0 > full_dst) full0 = full_dst;
+  if (full1 > full_dst) full1 = full_dst;
+  if (full0) cuda_check(cudaMemcpy2DAsync(out.first.gpu_data, sizeof(Fr_t) * w, gpu_data, sizeof(Fr_t) * 2 * w, sizeof(Fr_t) * w, full0, cudaMemcpyDeviceToDevice, cur_stream()));
+  if (full1) cuda_check(cudaMemcpy2DAsync(out.second.gpu_data, sizeof(Fr_t) * w, gpu_data + w, sizeof(Fr_t) * 2 * w, sizeof(Fr_t) * w, full1, cudaMemcpyDeviceToDevice, cur_stream()));
+  for (size_t wid = full1; wid * w < out_size; ++wid) {
+    size_t dst = wid * w, n0 = std::min<size_t>(w, out_size - dst);
+    size_t s0 = 2 * wid * w, s1 = s0 + w;
+    if (wid >= full0 && s0 < size) cuda_check(cudaMemcpyAsync(out.first.gpu_data + dst, gpu_data + s0, sizeof(Fr_t) * std::min<size_t>(n0, size - s0), cudaMemcpyDeviceToDevice, cur_stream()));
+    if (s1 < size) cuda_check(cudaMemcpyAsync(out.second.gpu_data + dst, gpu_data + s1, sizeof(Fr_t) * std::min<size_t>(n0, size - s1), cudaMemcpyDeviceToDevice, cur_stream()));
   }
+  sync();
   return out;
 }
 FrTensor FrTensor::partial_me(vector<Fr_t> u, uint window_size) const {

@@ -156,7 +156,10 @@ def verify_zkfc(proof_fr, proof_g1, G, B, I, O, u_bs, u_in, u_out, gens_table=No
 
 
 def verify_zkrelu(proof_fr, n, u_z, v_z, u_r, v_r, u_hp, v_hp):
-    """zkReLU::prove (zkrelu.cu:79-100): two binary sumchecks (claim 0) and the Hadamard sumcheck chain."""
+    """zkReLU::prove (zkrelu.cu:79-100): two binary sumchecks (claim 0) and the Hadamard sumcheck chain.  The 32 + 16
+    partial_me(u_recover, .) rows are evaluations at a point the binary sumchecks never visit, and the fragments carry neither
+    X~(u_recover) nor sign~(u_recover): the recover relation cannot be checked from the reference's proof elements, and the
+    Hadamard sumcheck's initial claim is implicit (accepted as the first round states it)."""
     fr = zk.to_host(proof_fr)
     L = (n - 1).bit_length()
     o = 0
