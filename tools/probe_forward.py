@@ -31,3 +31,8 @@ for _ in range(20):
     zk.relu_packed(Z)
 e1.record(); torch.cuda.synchronize()
 print(f"relu_packed 2^19 {e0.elapsed_time(e1) / 20:.3f} ms")
+e0.record()
+for _ in range(20):
+    zk.fr_matmul_prepared(X, L.mm, 256)
+e1.record(); torch.cuda.synchronize()
+print(f"fr_matmul_prepared 256x2048x2048 (quantise + route + tensor-core product) {e0.elapsed_time(e1) / 20:.3f} ms")

@@ -216,28 +216,105 @@ __global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, 
   if (threadIdx.x == 0) { proof3[0] = acc[0]; proof3[1] = acc[1]; proof3[2] = acc[2]; *counter = 0; }
 }
 
-// All remaining rounds in one CTA.  bufs: a0/a1 (and b0/b1) ping-pong, e0/e1 ping-pong.  xs = fold challenges for the
-// remaining rounds.  proof gets 3 values per round, then the final a[0] (and b[0]).
+// All remaining rounds (table of at most TAIL_N entries) in one CTA, entirely in shared memory: the table(s) and the eq table
+// are loaded once, every round folds them in place (compute into registers, barrier, write back, barrier: each thread owns
+// one double-pair), and the per-round coefficient sums are only reduced inside each warp; the per-warp partials of ALL rounds
+// are added up after the last round by 3 * rounds threads in parallel.  (The first version kept the tables in global memory
+// and ran a two-stage block reduction per round: 90-125 us for 11 rounds, all of it latency.)
+// proof gets 3 values per round, then the final a[0] (and b[0]).
+static constexpr int TAIL_WARPS = TAIL_THREADS / 32;
 template <int KIND>
-__global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(Fr* a0, Fr* a1, Fr* b0, Fr* b1, Fr* e0, Fr* e1, const Fr* __restrict__ xs,
-                                                          int rounds, size_t in_size, size_t esize, Fr* __restrict__ proof) {
-  __shared__ Fr sm[3 * 32];
-  Fr *a = a0, *an = a1, *b = b0, *bn = b1, *e = e0, *en = e1;
+static constexpr size_t tail_smem_bytes() {
+  return sizeof(Fr) * (TAIL_N + (KIND != SC_BIN ? TAIL_N : 0) + (KIND != SC_IP ? TAIL_N / 2 : 0) + 12 * TAIL_WARPS * 3);
+}
+extern __shared__ __align__(16) unsigned char tail_smem[];
+template <int KIND>
+__global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__ a_g, const Fr* __restrict__ b_g, const Fr* __restrict__ e_g,
+                                                          const Fr* __restrict__ xs, int rounds, size_t in_size, size_t esize, Fr* __restrict__ proof) {
+  Fr* sa = reinterpret_cast<Fr*>(tail_smem);
+  Fr* sb = sa + TAIL_N;
+  Fr* se = sb + (KIND != SC_BIN ? TAIL_N : 0);
+  Fr* red = se + (KIND != SC_IP ? TAIL_N / 2 : 0);                  // [round][warp][3]
+  __shared__ Fr sx[12];                                             // the remaining fold challenges
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < rounds) sx[tid] = xs[tid];
+  for (size_t i = tid; i < in_size; i += blockDim.x) { sa[i] = a_g[i]; if (KIND != SC_BIN) sb[i] = b_g[i]; }
+  if (KIND != SC_IP) for (size_t i = tid; i < esize; i += blockDim.x) se[i] = e_g[i];
+  __syncthreads();
+  const size_t in0 = in_size, es0 = esize;
   for (int j = 0; j < rounds; ++j) {
-    size_t out_size = (in_size + 1) / 2;
-    size_t H = (KIND != SC_IP && esize >= 2) ? esize / 2 : (out_size + 1) / 2;
-    Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
-    Fr x = xs[j];
-    sc_round_items<KIND>(a, b, an, bn, e, (KIND != SC_IP && esize >= 2) ? en : nullptr, x, in_size, out_size, H, threadIdx.x, blockDim.x, acc);
-    block_reduce_fr<3>(acc, sm);
-    if (threadIdx.x == 0) { proof[3 * j] = acc[0]; proof[3 * j + 1] = acc[1]; proof[3 * j + 2] = acc[2]; }
+    const size_t out_size = (in_size + 1) / 2;
+    const bool fold_e = (KIND != SC_IP) && esize >= 2;
+    const size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;     // <= TAIL_THREADS: one double-pair per thread
+    const int nact = (int)((H + 31) / 32);
+    Fr ao[2], bo[2], eo;
+    bool wr[2] = {false, false};
+    if (warp < nact) {
+      Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
+      const size_t h = tid;
+      if (h < H) {
+        const Fr x = sx[j];
+        Fr e0, e1;
+        if (KIND != SC_IP) {
+          e0 = se[2 * h];
+          if (fold_e) { e1 = se[2 * h + 1]; eo = add(e0, e1); } else e1 = Fr::zero();
+        }
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const size_t g = 2 * h + t;
+          if (g >= out_size) break;
+          const size_t g0 = 2 * g, g1 = 2 * g + 1;
+          Fr a0 = g0 < in_size ? sa[g0] : Fr::zero();
+          Fr a1 = g1 < in_size ? sa[g1] : Fr::zero();
+          Fr c[3];
+          if (KIND == SC_BIN) {
+            ao[t] = bin_pair(a0, a1, t ? e1 : e0, x, c);
+          } else {
+            Fr b0 = g0 < in_size ? sb[g0] : Fr::zero();
+            Fr b1 = g1 < in_size ? sb[g1] : Fr::zero();
+            if (KIND == SC_HP) ip_pair<true>(a0, a1, b0, b1, t ? e1 : e0, x, c, ao[t], bo[t]);
+            else ip_pair<false>(a0, a1, b0, b1, a0, x, c, ao[t], bo[t]);
+          }
+          wr[t] = true;
+          acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          Fr o;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, acc[c].v[i], off);
+          acc[c] = add(acc[c], o);
+        }
+      }
+      if (lane == 0) { Fr* r = red + ((size_t)j * TAIL_WARPS + warp) * 3; r[0] = acc[0]; r[1] = acc[1]; r[2] = acc[2]; }
+    }
+    __syncthreads();                                                // every read of this round's tables is done
+    if (warp < nact && (size_t)tid < H) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (wr[t]) { sa[2 * tid + t] = ao[t]; if (KIND != SC_BIN) sb[2 * tid + t] = bo[t]; }
+      if (fold_e) se[tid] = eo;
+    }
     __syncthreads();
-    Fr* t = a; a = an; an = t; t = b; b = bn; bn = t; t = e; e = en; en = t;
     in_size = out_size; esize = esize >= 2 ? esize / 2 : 1;
   }
-  if (threadIdx.x == 0) {
-    proof[3 * rounds] = a[0];
-    if (KIND != SC_BIN) proof[3 * rounds + 1] = b[0];
+  if (tid < 3 * rounds) {                                           // the deferred cross-warp sums, all rounds in parallel
+    const int j = tid / 3, c = tid % 3;
+    size_t n = in0, es = es0;
+    for (int r = 0; r < j; ++r) { n = (n + 1) / 2; es = es >= 2 ? es / 2 : 1; }
+    const size_t out_size = (n + 1) / 2;
+    const size_t H = ((KIND != SC_IP) && es >= 2) ? es / 2 : (out_size + 1) / 2;
+    const int nact = (int)((H + 31) / 32);
+    Fr sum = red[((size_t)j * TAIL_WARPS) * 3 + c];
+    for (int w = 1; w < nact; ++w) sum = add(sum, red[((size_t)j * TAIL_WARPS + w) * 3 + c]);
+    proof[3 * j + c] = sum;
+  }
+  if (tid == 0) {
+    proof[3 * rounds] = sa[0];
+    if (KIND != SC_BIN) proof[3 * rounds + 1] = sb[0];
   }
 }
 
@@ -400,7 +477,7 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   int which = 0, ewhich = 0;
   size_t j = 0;
   for (; j < k; ++j) {
-    if (cur_n <= TAIL_N && j > 0) break;                  // tail needs writable ping-pong buffers: at least one round done
+    if (cur_n <= TAIL_N) break;                           // the rest fits one CTA's shared memory
     size_t out_size = (cur_n + 1) / 2;
     bool fold_e = (KIND != SC_IP) && esize >= 2;
     size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
@@ -414,8 +491,12 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
     if (fold_e) { ewhich ^= 1; esize /= 2; }
   }
   if (j < k) {
-    ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_sc_tail<KIND><<<1, TAIL_THREADS, 0, st>>>(const_cast<Fr*>(ca), abuf[which], const_cast<Fr*>(cb), bbuf[which], ebuf[ewhich], ebuf[ewhich ^ 1],
-                                                          xs.as<Fr>() + j, (int)(k - j), cur_n, esize, proof + 3 * j));
+    static bool attr_done = false;                         // per kernel instantiation (function-local static of a template)
+    if (!attr_done) {
+      ZK_CUDA(cudaFuncSetAttribute(k_sc_tail<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem_bytes<KIND>()));
+      attr_done = true;
+    }
+    ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_sc_tail<KIND><<<1, TAIL_THREADS, tail_smem_bytes<KIND>(), st>>>(ca, cb, ebuf[ewhich], xs.as<Fr>() + j, (int)(k - j), cur_n, esize, proof + 3 * j));
   } else {
     ZK_CUDA(cudaMemcpyAsync(proof + 3 * k, ca, sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     if (KIND != SC_BIN) ZK_CUDA(cudaMemcpyAsync(proof + 3 * k + 1, cb, sizeof(Fr), cudaMemcpyDeviceToDevice, st));

@@ -608,7 +608,8 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   unsigned dgrid = g1_grid(m * cfg.n, 256);
   const bool few_keys = nkeys <= SMALL_KEYS;
   // chunked accumulation: about two resident waves of threads, each with the same number of mixed additions
-  uint32_t target = (uint32_t)num_sms() * 384 * 2;
+  static const double waves = getenv("ZKDL_MSM_WAVES") ? atof(getenv("ZKDL_MSM_WAVES")) : 2.0;   // tuning knob
+  uint32_t target = (uint32_t)(num_sms() * 384 * waves);
   const int G = nkeys <= 8192 ? 8 : 1;                          // combine lanes per bucket
   Scratch plan, heavy;
   if ((rc = plan.alloc(sizeof(uint32_t) * 2, st))) return rc;
