@@ -1,5 +1,6 @@
 #!/bin/bash
-# The drop-in ./demo (zkdl_b200/host/demo) and the reference ./demo (oracle/_ref/demo) on the full 18.2M-param model, batch 256.
+# The drop-in ./demo (zkdl_b200/host/demo) on the full 18.2M-param model, batch 256, for 0 (blocking loop) / 4 / 8 / 15 streams (cold first pass and
+# warm last pass of ZKDL_DEMO_REPS=3), and with "ref" the reference ./demo (oracle/_ref/demo) on the same files + both demo.out hashes.
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 W=$(mktemp -d); cd "$W"
@@ -18,6 +19,11 @@ x = torch.randn(256, 784).to("cuda")
 save_tensor(x, "sample_input.pt")
 torch.jit.trace(model, x[:1]).save("traced_model.pt")
 PY
-for i in 1 2 3; do SECONDS=0; $ROOT/zkdl_b200/host/demo traced_model.pt sample_input.pt 2>&1 | tr "\n" " "; echo " wall ${SECONDS}s"; done
-sha256sum demo.out | cut -c1-16
-if [ "$1" == "ref" ]; then $ROOT/oracle/_ref/demo traced_model.pt sample_input.pt 2>&1 | tr '\n' ' '; echo; sha256sum demo.out | cut -c1-16; fi
+for t in 0 4 8 15; do
+  SECONDS=0; echo -n "{\"streams\": $t, \"out\": \""; ZKDL_DEMO_STREAMS=$t ZKDL_DEMO_REPS=3 $ROOT/zkdl_b200/host/demo traced_model.pt sample_input.pt 2>&1 | tr "\n" " "; echo "\", \"wall_s\": $SECONDS}"
+done
+echo "{\"demo_out_sha256_ours\": \"$(sha256sum demo.out | cut -c1-64)\"}"
+if [ "$1" == "ref" ]; then
+  LD_LIBRARY_PATH=$(python -c 'import torch,os;print(os.path.dirname(torch.__file__))')/lib:$LD_LIBRARY_PATH $ROOT/oracle/_ref/demo traced_model.pt sample_input.pt 2>&1 | tr '\n' ' '; echo
+  echo "{\"demo_out_sha256_reference\": \"$(sha256sum demo.out | cut -c1-64)\"}"
+fi

@@ -100,9 +100,13 @@ static int reserve_one(cudaStream_t s, size_t bytes) {
   if (rc) return rc;
   return scratch_free(p, s);                     // ... and releases it (consolidating if it had several blocks)
 }
-SideStream& side_stream(int idx) {
-  static thread_local SideStream pool[4];
-  return pool[idx & 3];
+SideStream& side_stream(int idx, cudaStream_t main) {
+  struct Pool { SideStream s[4]; };
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, Pool> pools;       // node-based: references stay valid
+  int dev = 0; cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  return pools[{dev, main}].s[idx & 3];
 }
 int SideStream::fork(cudaStream_t main) {
   if (!stream) {
@@ -135,7 +139,7 @@ int zkdl_scratch_reserve(size_t bytes, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int rc = zk::reserve_one(st, bytes);
   for (int i = 0; i < 3 && !rc; ++i) {           // the side streams this host thread forks sub-proofs onto
-    zk::SideStream& ss = zk::side_stream(i);
+    zk::SideStream& ss = zk::side_stream(i, st);
     if ((rc = ss.fork(st))) break;
     rc = zk::reserve_one(ss.stream, bytes / 2);
     if (!rc) rc = ss.join(st);

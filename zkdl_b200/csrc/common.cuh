@@ -39,14 +39,15 @@ struct Scratch {                       // RAII helper used inside the C-ABI func
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-// Fork/join of independent sub-proofs onto side streams (per host thread): fork() makes side stream `idx` wait for the
-// work enqueued so far on `main`; join() makes `main` wait for everything enqueued on the side stream since.
+// Fork/join of independent sub-proofs onto side streams (a pool of 4 per main stream, so that proofs issued on different
+// main streams - from one host thread or several - never share a side stream): fork() makes side stream `idx` wait for
+// the work enqueued so far on `main`; join() makes `main` wait for everything enqueued on the side stream since.
 struct SideStream {
   cudaStream_t stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int fork(cudaStream_t main);
   int join(cudaStream_t main);
 };
-SideStream& side_stream(int idx);          // idx < 4
+SideStream& side_stream(int idx, cudaStream_t main);   // idx < 4; one pool per (device, main stream)
 // fork() now, join() on every way out of the scope: an early error return must not leave the side stream still reading
 // the caller's buffers while the caller frees them
 struct ForkScope {

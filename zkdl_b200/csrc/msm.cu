@@ -607,8 +607,9 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   ZK_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(uint32_t) * nkeys, st));
   unsigned dgrid = g1_grid(m * cfg.n, 256);
   const bool few_keys = nkeys <= SMALL_KEYS;
-  // chunked accumulation: about two resident waves of threads, each with the same number of mixed additions
-  static const double waves = getenv("ZKDL_MSM_WAVES") ? atof(getenv("ZKDL_MSM_WAVES")) : 2.0;   // tuning knob
+  // chunked accumulation: about one resident wave of threads (measured: 0.5 / 1 / 2 waves within 1 %; fewer chunks = fewer
+  // partials to combine), each with the same number of mixed additions
+  static const double waves = getenv("ZKDL_MSM_WAVES") ? atof(getenv("ZKDL_MSM_WAVES")) : 1.0;   // tuning knob
   uint32_t target = (uint32_t)(num_sms() * 384 * waves);
   const int G = nkeys <= 8192 ? 8 : 1;                          // combine lanes per bucket
   Scratch plan, heavy;
@@ -706,7 +707,7 @@ int open_run(const zkdl_g1_table* gens, const zkdl_g1_table* com_table, const Fr
   if (khi > 0) ZK_REQUIRE(!(ncom <= ((size_t)1 << (khi - 1)) || ncom > ((size_t)1 << khi)), ZK_ERR_DIM, "Incompatible dimensions");
   // com(u_hi) and the opening proper are independent: fork the commitment-vector evaluation onto a side stream so its
   // latency-bound bucket reduction overlaps the opening MSM (joined before returning).
-  SideStream& ss = side_stream(0);
+  SideStream& ss = side_stream(0, st);
   Scratch uq, E, tf; int rc;
   ForkScope fs(ss, st);
   if ((rc = fs.fork())) return rc;

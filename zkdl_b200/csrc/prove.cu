@@ -43,7 +43,7 @@ int zkdl_zkfc_prove_parts(const zkdl_fr_t* X, const zkdl_fr_t* W, const zkdl_mm_
   ZK_REQUIRE(((size_t)1 << kb) == B && ((size_t)1 << ki) == I && ((size_t)1 << ko) == O, ZK_ERR_DIM, "Incompatible dimensions 1");
   int rc;
   // The matmul sumcheck and the commitment opening are independent: the sumcheck part runs on a side stream.
-  SideStream& ss = side_stream(1);
+  SideStream& ss = side_stream(1, st);
   ForkScope fs(ss, st);
   if ((rc = fs.fork())) return rc;
   void* sst = reinterpret_cast<void*>(ss.stream);

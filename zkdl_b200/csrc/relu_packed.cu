@@ -358,7 +358,7 @@ int zkdl_zkrelu_prove_packed_parts(const zkdl_fr_t* X, const zkdl_fr_t* sign, co
   Fr* p_rem_sc = p;                       p += 3 * (L + 4) + 1;
   Fr* p_rem_rec = p;                      p += 16;
   // the three sumchecks are independent: mag_bin on the caller's stream, rem_bin and the Hadamard product on side streams
-  SideStream& s1 = side_stream(1); SideStream& s2 = side_stream(2);
+  SideStream& s1 = side_stream(1, st); SideStream& s2 = side_stream(2, st);
   ForkScope f1(s1, st), f2(s2, st);
   if ((rc = f1.fork())) return rc;
   if ((rc = f2.fork())) return rc;

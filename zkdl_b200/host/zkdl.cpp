@@ -34,6 +34,10 @@ void zkdl_host::copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind ki
   cuda_check(cudaStreamSynchronize(t_stream));
 }
 
+static std::atomic<bool> g_async_prove{false};
+void zkdl_host::set_async_prove(bool on) { g_async_prove = on; }
+bool zkdl_host::async_prove() { return g_async_prove.load(); }
+
 // ------------------------------------------------------------------------------------------------ challenge seeds
 static std::atomic<uint32_t> g_seed_base{0}, g_seed_ctr{0};
 static thread_local uint32_t t_seed_base = 0, t_seed_ctr = 0;
@@ -389,15 +393,26 @@ void zkFC::prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) c
   auto u_out = random_vec(ceilLog2(outputSize));
   size_t nfr, ng1;
   zkdl_zkfc_proof_sizes(B, inputSize, outputSize, generators.size, &nfr, &ng1);
-  FrTensor pfr((uint)nfr); G1TensorJacobian pg1((uint)ng1);
+  if (!pbuf_ || pbuf_->nfr != nfr || pbuf_->ng1 != ng1) {               // first proof of this object (or a new shape): plain cudaMalloc, kept
+    pbuf_ = std::make_shared<ProofBuf>();
+    cuda_check(cudaMalloc(&pbuf_->fr, sizeof(Fr_t) * nfr)); cuda_check(cudaMalloc(&pbuf_->g1, sizeof(G1Jacobian_t) * ng1));
+    pbuf_->nfr = nfr; pbuf_->ng1 = ng1;
+  }
   // the integer copy of the weights exists once operator() has run (the forward pass precedes the proof, demo.cu:116-138)
   check(zkdl_zkfc_prove_parts(X.gpu_data, weights.gpu_data, mm_ ? mm_->w : nullptr, Z.gpu_data, B, inputSize, outputSize,
-                              generators.table(), com.table(), u_bs.data(), u_in.data(), u_out.data(), pfr.gpu_data, pg1.gpu_data,
+                              generators.table(), com.table(), u_bs.data(), u_in.data(), u_out.data(), pbuf_->fr, pbuf_->g1,
                               ZKDL_FC_SUMCHECK | ZKDL_FC_OPENING, st()));
-  sync();
-  proof_fr_ = download(pfr);
-  proof_g1_.resize(ng1);
-  copy(proof_g1_.data(), pg1.gpu_data, sizeof(G1Jacobian_t) * ng1, cudaMemcpyDeviceToHost);
+  pbuf_->stream = cur_stream(); pbuf_->pending = true;
+  if (!async_prove()) fetch_proof();
+}
+zkFC::ProofBuf::~ProofBuf() { cudaFree(fr); cudaFree(g1); }
+void zkFC::fetch_proof() const {
+  if (!pbuf_ || !pbuf_->pending) return;
+  cuda_check(cudaStreamSynchronize(pbuf_->stream));
+  proof_fr_.resize(pbuf_->nfr); proof_g1_.resize(pbuf_->ng1);
+  cuda_check(cudaMemcpy(proof_fr_.data(), pbuf_->fr, sizeof(Fr_t) * pbuf_->nfr, cudaMemcpyDeviceToHost));
+  cuda_check(cudaMemcpy(proof_g1_.data(), pbuf_->g1, sizeof(G1Jacobian_t) * pbuf_->ng1, cudaMemcpyDeviceToHost));
+  pbuf_->pending = false;
 }
 
 // ------------------------------------------------------------------------------------------------ zkReLU
@@ -412,6 +427,7 @@ void zkReLU::reset_ptrs(uint size) {                                            
 zkReLU::~zkReLU() {
   delete sign_ptr; delete mag_bin_ptr; delete rem_bin_ptr; sign_ptr = mag_bin_ptr = rem_bin_ptr = nullptr;
   dev_free(mag_packed_); dev_free(rem_packed_); mag_packed_ = nullptr; rem_packed_ = nullptr;
+  cudaFree(dev_proof_); dev_proof_ = nullptr;
 }
 FrTensor zkReLU::operator()(const FrTensor& X) {                                                                        // zkrelu.cu:44-51
   reset_ptrs(X.size);
@@ -427,9 +443,17 @@ void zkReLU::prove(const FrTensor& X, const FrTensor& Z) {                      
   uint L = ceilLog2(X.size);
   auto u_z = random_vec(L + 5), v_z = random_vec(L + 5), u_r = random_vec(L + 4), v_r = random_vec(L + 4), u_rec = random_vec(L);
   auto u_hp = random_vec(L), v_hp = random_vec(L);
-  FrTensor p((uint)zkdl_zkrelu_proof_size(X.size));
+  const size_t np = zkdl_zkrelu_proof_size(X.size);
+  if (!dev_proof_ || dev_proof_n_ != np) { cudaFree(dev_proof_); cuda_check(cudaMalloc(&dev_proof_, sizeof(Fr_t) * np)); dev_proof_n_ = np; }
   check(zkdl_zkrelu_prove_packed(X.gpu_data, sign_ptr->gpu_data, mag_packed_, rem_packed_, X.size, u_z.data(), v_z.data(), u_r.data(),
-                                 v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), p.gpu_data, st()));
-  sync();
-  proof_ = download(p);
+                                 v_r.data(), u_rec.data(), u_hp.data(), v_hp.data(), dev_proof_, st()));
+  proof_stream_ = cur_stream(); proof_pending_ = true;
+  if (!async_prove()) fetch_proof();
+}
+void zkReLU::fetch_proof() {
+  if (!proof_pending_) return;
+  cuda_check(cudaStreamSynchronize(proof_stream_));
+  proof_.resize(dev_proof_n_);
+  cuda_check(cudaMemcpy(proof_.data(), dev_proof_, sizeof(Fr_t) * dev_proof_n_, cudaMemcpyDeviceToHost));
+  proof_pending_ = false;
 }

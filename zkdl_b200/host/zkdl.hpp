@@ -51,6 +51,13 @@ void dev_free(void* p);
 template <class T> T* dev_alloc(size_t n) { return static_cast<T*>(dev_alloc_bytes(sizeof(T) * (n ? n : 1))); }
 void copy(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);        // on cur_stream(), synchronised
 uint32_t next_challenge_seed();        // random_device, or a counter when set_challenge_seed() was called
+// zkFC::prove / zkReLU::prove return nothing observable in the reference (the proof vectors are dropped, zkfc.cu:139-144).
+// With async proves ON they only ENQUEUE the proof on the calling thread's current stream (no allocation, no host
+// synchronisation after the object's first proof); last_proof_*() synchronises that stream and downloads on demand.  A host
+// loop can thus spread independent layer proofs over several streams from ONE thread (demo.cpp).  Default: OFF (a prove()
+// call returns with the proof finished, like every other shim call).
+void set_async_prove(bool on);
+bool async_prove();
 }  // namespace zkdl_host
 
 void set_challenge_seed(uint32_t seed);   // 0 restores std::random_device
@@ -201,6 +208,9 @@ class zkFC {
   G1TensorJacobian com;
   mutable std::vector<Fr_t> proof_fr_;
   mutable std::vector<G1Jacobian_t> proof_g1_;
+  struct ProofBuf { Fr_t* fr = nullptr; G1Jacobian_t* g1 = nullptr; size_t nfr = 0, ng1 = 0; cudaStream_t stream = 0; bool pending = false; ~ProofBuf(); };
+  mutable std::shared_ptr<ProofBuf> pbuf_;       // device proof buffers, allocated by the first prove() and reused
+  void fetch_proof() const;
   struct MMHolder { zkdl_mm_weights* w = nullptr; ~MMHolder(); };
   mutable std::shared_ptr<MMHolder> mm_;         // quantised integer copy of `weights` for operator(), shared by copies
  public:
@@ -211,8 +221,8 @@ class zkFC {
   void prove(const FrTensor& X, const FrTensor& Z, Commitment& generators) const;
   static zkFC from_float_gpu_ptr(uint input_size, uint output_size, float* float_gpu_ptr, const Commitment& generators);
   static FrTensor load_float_gpu_input(uint batch_size, uint input_dim, float* input_ptr);
-  const std::vector<Fr_t>& last_proof_fr() const { return proof_fr_; }
-  const std::vector<G1Jacobian_t>& last_proof_g1() const { return proof_g1_; }
+  const std::vector<Fr_t>& last_proof_fr() const { fetch_proof(); return proof_fr_; }
+  const std::vector<G1Jacobian_t>& last_proof_g1() const { fetch_proof(); return proof_g1_; }
   const G1TensorJacobian& commitment() const { return com; }
 };
 
@@ -223,6 +233,8 @@ class zkReLU {
   FrTensor* rem_bin_ptr = nullptr;
   void reset_ptrs(uint size);
   std::vector<Fr_t> proof_;
+  Fr_t* dev_proof_ = nullptr; size_t dev_proof_n_ = 0; cudaStream_t proof_stream_ = 0; bool proof_pending_ = false;
+  void fetch_proof();
   uint32_t* mag_packed_ = nullptr;               // the same auxiliary input, 48 bits per activation (device)
   uint16_t* rem_packed_ = nullptr;
   uint n_ = 0;
@@ -235,7 +247,7 @@ class zkReLU {
   FrTensor operator()(const FrTensor& X);
   void prove(const FrTensor& X, const FrTensor& Z);
   ~zkReLU();
-  const std::vector<Fr_t>& last_proof() const { return proof_; }
+  const std::vector<Fr_t>& last_proof() { fetch_proof(); return proof_; }
 };
 
 // ------------------------------------------------------------------------------------------------ Timer (timer.hpp)
