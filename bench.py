@@ -490,6 +490,20 @@ def main():
         extra["msm_mpts_s_plain_2^16"] = sweep["2^16"]["Mpts_per_s_255bit"]
         extra["msm_mpts_s_fixed_base_2^16"] = sweep["2^16"]["Mpts_per_s_255bit_fixed_base"]
         extra["msm_mpts_s_plain_2^24"] = sweep["2^24"]["Mpts_per_s_255bit"]
+        # ---- the named drop-in entry: the C++ ./demo (zkdl_b200/host/demo) on the same model, timed by its own Timer
+        demo_bin = os.path.join(ROOT, "zkdl_b200", "host", "demo")
+        if os.path.exists(demo_bin):
+            try:
+                tmp = tempfile.mkdtemp(prefix="zkdl_demo_")
+                subprocess.check_call([sys.executable, "-c", MODEL_GEN, str(BATCH)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                env = dict(os.environ, ZKDL_DEMO_REPS="3", LD_LIBRARY_PATH=os.path.join(os.path.dirname(torch.__file__), "lib") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+                out = subprocess.run([demo_bin, "traced_model.pt", "sample_input.pt"], cwd=tmp, env=env, capture_output=True, text=True, timeout=300)
+                m = re.search(r"Proof time: ([0-9.eE+-]+) seconds per data point", out.stdout)
+                c = re.search(r"cold pass of the same proof: ([0-9.eE+-]+) seconds", out.stdout)
+                extra["demo_cpp_ms"] = float(m.group(1)) * BATCH * 1e3 if m else None
+                extra["demo_cpp_cold_first_pass_ms"] = float(c.group(1)) * BATCH * 1e3 if c else None
+            except Exception as ex:      # the C++ entry is reported, not required, by the Python bench
+                extra["demo_cpp_ms"] = None; extra["demo_cpp_error"] = repr(ex)[:200]
     L2 = P.layers[2]
     extra["commit_2048x2048_ms"] = timed(lambda: zk.commit(L2.gens, L2.W), reps=3, warm=1)
     extra["commit_msm_mpts_s"] = (L2.I * L2.O) / (extra["commit_2048x2048_ms"] * 1e-3) / 1e6

@@ -62,6 +62,12 @@ int zkdl_fr_me(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, 
 size_t zkdl_partial_me_size(size_t n, size_t k, size_t window);
 int zkdl_fr_partial_me(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t window, zkdl_fr_t* out, void* stream);
 
+/* FrTensor::random / FrTensor::random_int (fr-tensor.cu:302-368): the reference's generator (curand XORWOW, one state per
+ * element, curand_init(seed, index, 0)); same seed -> bit-identical tables.  random: 8 draws per element, top limb
+ * % 0x73eda753 (value < p, read as Montgomery or plain by the caller); random_int: (draw & (2^num_bits - 1)) - 2^(num_bits-1). */
+int zkdl_fr_random(zkdl_fr_t* out, size_t n, uint64_t seed, void* stream);
+int zkdl_fr_random_int(zkdl_fr_t* out, uint32_t num_bits, size_t n, uint64_t seed, void* stream);
+
 /* ------------------------------------------------------------------ sumchecks (proof.cu) */
 /* inner_product_sumcheck (proof.cu:72-108): proof gets 3k+2 Fr */
 int zkdl_ip_sumcheck(const zkdl_fr_t* a, const zkdl_fr_t* b, size_t n, const zkdl_fr_t* u_host, size_t k, zkdl_fr_t* proof, void* stream);

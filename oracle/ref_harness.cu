@@ -325,6 +325,18 @@ int main(int argc, char** argv) {
         auto pr = a.split(w);
         out["split." + std::to_string(w) + ".first"] = fr_out(pr.first); out["split." + std::to_string(w) + ".second"] = fr_out(pr.second);
       }
+    } else if (what == "random") {      // full random <n> <seed> <out.bin>: FrTensor::random / random_int's kernels with a fixed seed
+      uint n = atoi(argv[3]); unsigned long seed = strtoul(argv[4], nullptr, 10);
+      FrTensor a(n), b(n);
+#ifndef ZKDL_HOST_BUILD
+      random_kernel<<<(n + 255) / 256, 256>>>(a.gpu_data, n - 1, seed);                // `tid > n` guard (fr-tensor.cu:342): n - 1 writes exactly n elements
+      random_int_kernel<<<(n + 255) / 256, 256>>>(b.gpu_data, 13, n, seed + 1);
+      cudaDeviceSynchronize();
+#else
+      zkdl_fr_random(a.gpu_data, n, seed, 0); zkdl_fr_random_int(b.gpu_data, 13, n, seed + 1, 0);
+      cudaDeviceSynchronize();
+#endif
+      out["random.fr"] = fr_out(a); out["random.int13"] = fr_out(b);
     } else { fprintf(stderr, "unknown full case\n"); return 1; }
     out["cuda_status"] = std::vector<uint32_t>(1, (uint32_t)cudaGetLastError());
     write_box(argv[5], out);

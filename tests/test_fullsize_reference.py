@@ -199,3 +199,9 @@ def test_split_against_reference(zk, tmp_path):
     """FrTensor::split (fr-tensor.cu:376-397) of the drop-in shim (two strided 2-D copies + ragged tail) on a ragged table,
     windows 64 / 1 / 7 / n-1, against the reference's kernel."""
     compare_boxes(run_harness(REF, tmp_path, "ref", "split", 12, 64), run_harness(TWIN, tmp_path, "twin", "split", 12, 64))
+
+
+def test_random_generator_against_reference(zk, tmp_path):
+    """FrTensor::random / random_int (fr-tensor.cu:302-347): the reference's kernels launched with a fixed seed against
+    zkdl_fr_random / zkdl_fr_random_int (curand XORWOW, curand_init(seed, index, 0)), 5000 elements (ragged last CTA)."""
+    compare_boxes(run_harness(REF, tmp_path, "ref", "random", 5000, 123456789), run_harness(TWIN, tmp_path, "twin", "random", 5000, 123456789))

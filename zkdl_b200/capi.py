@@ -205,6 +205,20 @@ def bin_sumcheck(a, u_host, v_host):
     return proof
 
 
+def fr_random(n, seed):
+    """FrTensor::random (fr-tensor.cu:337-368) with an explicit 64-bit seed: the reference's curand XORWOW stream."""
+    out = empty(n, 8)
+    _check(lib().zkdl_fr_random(_ptr(out), _sz(n), C.c_uint64(int(seed)), _stream()))
+    return out
+
+
+def fr_random_int(n, num_bits, seed):
+    """FrTensor::random_int (fr-tensor.cu:302-335) with an explicit seed."""
+    out = empty(n, 8)
+    _check(lib().zkdl_fr_random_int(_ptr(out), C.c_uint32(num_bits), _sz(n), C.c_uint64(int(seed)), _stream()))
+    return out
+
+
 def float_to_fr(fs, rows_out, cols_out):
     """fs: float32 CUDA tensor [rows, cols] -> Fr [rows_out*cols_out, 8] (not Montgomery)."""
     fs = fs.contiguous()

@@ -277,8 +277,20 @@ __global__ void __launch_bounds__(THREADS) k_w_planes(const int32_t* __restrict_
 // Fr_partial_me_step folds (a multilinear evaluation is the eq-weighted sum) at ~1/10 of its multiplications.
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
 
-__device__ __forceinline__ void isum_mac_signed(ISum& pos, ISum& neg, int32_t w, const Fr& e) {
-  if (w >= 0) isum_mac(pos, (uint32_t)w, e); else isum_mac(neg, 0u - (uint32_t)w, e);
+// Signed weights without a sign branch: w + 2^31 is an unsigned 32-bit factor, so
+//   sum_i w_i E_i = sum_i (w_i + 2^31) E_i - 2^31 sum_i E_i,
+// one accumulator and one correction per output.  Over a complete eq table sum_i E_i = 1 (Montgomery one), so the correction
+// is the constant mont(2^31); a zero-padded (partial) row range sums the E it covers.  (The first version kept separate
+// positive / negative accumulators: the divergent pair cost ~100 instructions per multiply-add.)
+__device__ __forceinline__ uint32_t w_offset(int32_t w) { return (uint32_t)w ^ 0x80000000u; }
+__device__ __forceinline__ Fr offset_correction(const Fr& esum) {        // 2^31 * esum mod p
+  ISum z; isum_zero(z); isum_mac(z, 0x80000000u, esum); return isum_reduce(z);
+}
+__device__ __forceinline__ void isum_add_fr(ISum& a, const Fr& e) {
+  uint64_t c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { uint64_t t = (uint64_t)a.v[j] + e.v[j] + c; a.v[j] = (uint32_t)t; c = t >> 32; }
+  uint64_t t = (uint64_t)a.v[8] + c; a.v[8] = (uint32_t)t; a.v[9] += (uint32_t)(t >> 32);
 }
 __device__ __forceinline__ ISum isum_shfl_down(const ISum& a, int d) {
   ISum r;
@@ -286,38 +298,43 @@ __device__ __forceinline__ ISum isum_shfl_down(const ISum& a, int d) {
   for (int j = 0; j < 10; ++j) r.v[j] = __shfl_down_sync(0xffffffffu, a.v[j], d);
   return r;
 }
-// window 1: out[r] = sum_c w[r][c] * E[c]; one warp per row
+// window 1: out[r] = sum_c w[r][c] * E[c], c over the WHOLE eq table (cols = 2^k); one warp per row
 __global__ void __launch_bounds__(256) k_wfold_cols(const int32_t* __restrict__ w, const Fr* __restrict__ E, size_t rows, size_t cols, Fr* __restrict__ out) {
   const int lane = threadIdx.x & 31;
+  const Fr corr = offset_correction(Fr::one());
   for (size_t r = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += (size_t)gridDim.x * (blockDim.x >> 5)) {
-    ISum pos, neg; isum_zero(pos); isum_zero(neg);
+    ISum acc; isum_zero(acc);
     const int32_t* row = w + r * cols;
-    for (size_t c = lane; c < cols; c += 32) isum_mac_signed(pos, neg, row[c], E[c]);
-    for (int d = 16; d > 0; d >>= 1) {
-      ISum op = isum_shfl_down(pos, d), on = isum_shfl_down(neg, d);
-      isum_add(pos, op); isum_add(neg, on);
-    }
-    if (lane == 0) out[r] = sub(isum_reduce(pos), isum_reduce(neg));
+    for (size_t c = lane; c < cols; c += 32) isum_mac(acc, w_offset(row[c]), E[c]);
+    for (int d = 16; d > 0; d >>= 1) { ISum o = isum_shfl_down(acc, d); isum_add(acc, o); }
+    if (lane == 0) out[r] = sub(isum_reduce(acc), corr);
   }
 }
-// window W: partial[(s * W + c) * 2 + {0,1}] = sum over the rows of slice s of w[r][c] * E[r]  (pos / neg)
+// window W: partial[s * W + c] = sum over the rows of slice s of (w[r][c] + 2^31) * E[r]
 __global__ void __launch_bounds__(128) k_wfold_rows(const int32_t* __restrict__ w, const Fr* __restrict__ E, size_t rows, size_t W, int slices,
                                                     ISum* __restrict__ partial) {
   const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const int s = blockIdx.y;
   if (c >= W) return;
   const size_t per = (rows + slices - 1) / slices, r0 = s * per, r1 = r0 + per < rows ? r0 + per : rows;
-  ISum pos, neg; isum_zero(pos); isum_zero(neg);
-  for (size_t r = r0; r < r1; ++r) isum_mac_signed(pos, neg, w[r * W + c], E[r]);
-  partial[((size_t)s * W + c) * 2] = pos;
-  partial[((size_t)s * W + c) * 2 + 1] = neg;
+  ISum acc; isum_zero(acc);
+  for (size_t r = r0; r < r1; ++r) isum_mac(acc, w_offset(w[r * W + c]), E[r]);
+  partial[(size_t)s * W + c] = acc;
 }
-__global__ void __launch_bounds__(128) k_wfold_rows_final(const ISum* __restrict__ partial, size_t W, int slices, Fr* __restrict__ out) {
+// full: the rows cover the whole eq table (sum E = 1); otherwise the covered E are summed here (cold path)
+__global__ void __launch_bounds__(128) k_wfold_rows_final(const ISum* __restrict__ partial, const Fr* __restrict__ E, size_t rows, size_t W, int slices,
+                                                          int full, Fr* __restrict__ out) {
   const size_t c = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (c >= W) return;
-  ISum pos = partial[c * 2], neg = partial[c * 2 + 1];
-  for (int s = 1; s < slices; ++s) { isum_add(pos, partial[((size_t)s * W + c) * 2]); isum_add(neg, partial[((size_t)s * W + c) * 2 + 1]); }
-  out[c] = sub(isum_reduce(pos), isum_reduce(neg));
+  ISum acc = partial[c];
+  for (int s = 1; s < slices; ++s) isum_add(acc, partial[(size_t)s * W + c]);
+  Fr esum = Fr::one();
+  if (!full) {
+    ISum es; isum_zero(es);
+    for (size_t r = 0; r < rows; ++r) isum_add_fr(es, E[r]);
+    esum = isum_reduce(es);
+  }
+  out[c] = sub(isum_reduce(acc), offset_correction(esum));
 }
 
 bool mmw_usable(const zkdl_mm_weights* p, size_t n) {
@@ -349,10 +366,10 @@ int wfold_rows(const zkdl_mm_weights* p, size_t window, const zkdl_fr_t* u_host,
   Scratch ud, E, part; int rc;
   if ((rc = eq_for(u_host, k, ud, E, st))) return rc;
   int slices = rows >= 32 ? 32 : (int)rows;
-  if ((rc = part.alloc(sizeof(ISum) * 2 * slices * window, st))) return rc;
+  if ((rc = part.alloc(sizeof(ISum) * slices * window, st))) return rc;
   dim3 grid(div_up(window, 128), slices);
   ZK_LAUNCH(k_wfold_rows<<<grid, 128, 0, st>>>(p->w32, E.as<Fr>(), rows, window, slices, part.as<ISum>()));
-  ZK_LAUNCH(k_wfold_rows_final<<<div_up(window, 128), 128, 0, st>>>(part.as<ISum>(), window, slices, out));
+  ZK_LAUNCH(k_wfold_rows_final<<<div_up(window, 128), 128, 0, st>>>(part.as<ISum>(), E.as<Fr>(), rows, window, slices, rows == ((size_t)1 << k) ? 1 : 0, out));
   return ZK_OK;
 }
 

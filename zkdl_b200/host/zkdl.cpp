@@ -1,6 +1,8 @@
 // zkdl.cpp — implementation of the host-side API mirror (zkdl.hpp) over the C ABI.  Plain C++ (g++), no kernels.
 #include "zkdl.hpp"
 #include <atomic>
+#include <climits>
+#include <random>
 
 using std::vector;
 using namespace zkdl_host;
@@ -161,18 +163,22 @@ FrTensor Fr_partial_me(const FrTensor& t, vector<Fr_t>::const_iterator begin, ve
   if (begin >= end) return t;
   return t.partial_me(vector<Fr_t>(begin, end), window_size);
 }
-FrTensor FrTensor::random_int(uint size, uint num_bits) {                          // fr-tensor.cu:302-335 (host RNG instead of curand)
+// The reference's generator (curand XORWOW, curand_init(seed, index, 0)) through the C ABI; the 64-bit seed comes from
+// std::random_device + mt19937_64 as in the reference (fr-tensor.cu:319-329), or from the injected seed stream.
+static unsigned long random_seed64() {
   std::mt19937_64 rng(next_challenge_seed());
-  vector<Fr_t> h(size);
-  for (uint i = 0; i < size; ++i) { h[i] = Fr_ZERO; h[i].val[0] = (uint32_t)rng() & ((1u << num_bits) - 1u); }
-  FrTensor out(size, h.data());
-  Fr_t half = Fr_ZERO; half.val[0] = 1u << (num_bits - 1);
-  return out - half;
+  std::uniform_int_distribution<unsigned long> distribution(0, ULONG_MAX);
+  return distribution(rng);
+}
+FrTensor FrTensor::random_int(uint size, uint num_bits) {                          // fr-tensor.cu:302-335
+  FrTensor out(size);
+  check(zkdl_fr_random_int(out.gpu_data, num_bits, size, random_seed64(), st())); sync();
+  return out;
 }
 FrTensor FrTensor::random(uint size) {                                              // fr-tensor.cu:337-368
-  vector<Fr_t> h(size);
-  zkdl_random_vec_host(next_challenge_seed(), size, h.data());
-  return FrTensor(size, h.data());
+  FrTensor out(size);
+  check(zkdl_fr_random(out.gpu_data, size, random_seed64(), st())); sync();
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------ G1TensorAffine

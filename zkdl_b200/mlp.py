@@ -43,9 +43,8 @@ class MLPProver:
             L.in_dim, L.out_dim = int(w.shape[0]), int(w.shape[1])
             L.I, L.O = pad2(L.in_dim), pad2(L.out_dim)
             L.ngens = 1 << ((ceil_log2(L.in_dim * L.out_dim) + 1) // 2)                      # demo.cu:81
-            ks = rng.integers(0, 1 << 32, size=(L.ngens, 8), dtype=np.uint64).astype(np.uint32)
-            ks[:, 7] %= 1944954707                                                           # fr-tensor.cu:346
-            L.G = zk.g1_mul(gen, zk.to_device(ks))                                           # generators *= random (demo.cu:82)
+            # generators *= FrTensor::random(n) (demo.cu:82): the reference's curand stream, seeded per layer
+            L.G = zk.g1_mul(gen, zk.fr_random(L.ngens, int(rng.integers(0, 1 << 63))))
             L.gens = zk.G1Table(L.G, full=True)
             q = zk.float_to_fr(w.contiguous(), L.I, L.O)                                     # zkfc.cu:90-100
             L.W = zk.fr_elementwise(zk.OP_MONT, q, out=q)
