@@ -76,6 +76,17 @@ int zkdl_hp_sumcheck(const zkdl_fr_t* a, const zkdl_fr_t* b, size_t n, const zkd
 /* binary_sumcheck (proof.cu:152-200): proof gets 3k+1 Fr */
 int zkdl_bin_sumcheck(const zkdl_fr_t* a, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, zkdl_fr_t* proof, void* stream);
 
+/* The same three sumchecks with a Fiat-Shamir transcript on the device (no reference counterpart: the reference draws every
+ * challenge from std::random_device up front, proof.cu:3-11, and its proofs bind to nothing).
+ * state_in_host: 32 transcript bytes.  Round j: S <- SHA-256(S || c0 || c1 || c2) over the 32-byte little-endian limb images of
+ * the round's proof elements; the fold challenge x_j = the digest's 8 little-endian u32 limbs, top limb % 0x73eda753 (the
+ * random_vec recipe).  proof: same layout and field elements as zkdl_{ip,hp,bin}_sumcheck would give for those challenges
+ * (for kind IP the challenges play the role of u, for HP / BIN of v; u_host is the eq point, fixed before round 0).
+ * challenges[k] and state_out[8] (big-endian digest words) are DEVICE outputs. */
+enum { ZKDL_FS_IP = 0, ZKDL_FS_HP = 1, ZKDL_FS_BIN = 2 };
+int zkdl_sumcheck_fs(int kind, const zkdl_fr_t* a, const zkdl_fr_t* b, size_t n, const zkdl_fr_t* u_host, size_t k, const uint8_t* state_in_host,
+                     zkdl_fr_t* proof, zkdl_fr_t* challenges, uint32_t* state_out, void* stream);
+
 /* ------------------------------------------------------------------ zkFC / zkReLU forward (zkfc.cu, zkrelu.cu) */
 /* float_to_Fr_kernel (zkfc.cu:63-88): round(x*2^16) -> signed Fr, NOT Montgomery; zero-pads to rows_out x cols_out */
 int zkdl_float_to_fr(const float* fs, zkdl_fr_t* out, uint32_t rows_in, uint32_t rows_out, uint32_t cols_in, uint32_t cols_out, void* stream);

@@ -219,6 +219,24 @@ def fr_random_int(n, num_bits, seed):
     return out
 
 
+FS_IP, FS_HP, FS_BIN = 0, 1, 2
+
+
+def sumcheck_fs(kind, a, b, u_eq, k, state):
+    """zkdl_sumcheck_fs: a sumcheck whose fold challenges come from a SHA-256 transcript ON THE DEVICE.  state: 32 bytes.
+    Returns (proof [3k + 1|2, 8], challenges [k, 8], state_out bytes) - reading the last two synchronises the stream."""
+    import numpy as np
+    torch = _torch()
+    nfin = 1 if kind == FS_BIN else 2
+    proof, xs = empty(3 * k + nfin, 8), empty(max(k, 1), 8)
+    st_out = torch.empty(8, dtype=torch.int32, device="cuda")
+    keep, up = _host_fr(u_eq if (u_eq is not None and len(u_eq)) else None)
+    sb = (C.c_uint8 * 32).from_buffer_copy(bytes(state))
+    _check(lib().zkdl_sumcheck_fs(C.c_int(kind), _ptr(a), _ptr(b), _sz(a.shape[0]), up, _sz(k), sb, _ptr(proof), _ptr(xs), _ptr(st_out), _stream()))
+    words = st_out.cpu().numpy().view(np.uint32)                   # big-endian digest words
+    return proof, xs[:k], b"".join(int(w).to_bytes(4, "big") for w in words)
+
+
 def float_to_fr(fs, rows_out, cols_out):
     """fs: float32 CUDA tensor [rows, cols] -> Fr [rows_out*cols_out, 8] (not Montgomery)."""
     fs = fs.contiguous()

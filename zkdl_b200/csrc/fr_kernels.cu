@@ -216,98 +216,6 @@ __global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, 
   if (threadIdx.x == 0) { proof3[0] = acc[0]; proof3[1] = acc[1]; proof3[2] = acc[2]; *counter = 0; }
 }
 
-// THREE rounds in one pass (all challenges are known up front): thread q owns entries [8q, 8q + 8), i.e. pairs 4q..4q+3 of
-// round j, pairs 2q, 2q+1 of round j+1 and pair q of round j+2, evaluated depth-first so that at most one folded value per
-// level is live.  The eq weights of the later rounds are the pair sums of the earlier ones (e'[h] = e[2h] + e[2h+1]); the
-// table after the third round pairs neighbouring threads' weights, hence the lane shuffle.  Used for mid-size tables, where
-// a round is latency- rather than throughput-bound: 3 launches and 3 passes over HBM become one.  Entries beyond in_size are
-// zero (the reference's padding rule, fr-tensor.cu:404-408), and zero pairs contribute zero to every coefficient.
-// partials[blockIdx][9]; the last CTA adds them up and writes the 9 proof elements.
-template <int KIND>
-__device__ __forceinline__ void sc3_pair(const Fr* __restrict__ a, const Fr* __restrict__ b, size_t g, size_t in_size, const Fr& e, const Fr& x,
-                                         Fr* acc, Fr& fa, Fr& fb) {
-  const size_t g0 = 2 * g, g1 = 2 * g + 1;
-  Fr a0 = g0 < in_size ? a[g0] : Fr::zero();
-  Fr a1 = g1 < in_size ? a[g1] : Fr::zero();
-  Fr c[3];
-  if (KIND == SC_BIN) {
-    fa = bin_pair(a0, a1, e, x, c);
-  } else {
-    Fr b0 = g0 < in_size ? b[g0] : Fr::zero();
-    Fr b1 = g1 < in_size ? b[g1] : Fr::zero();
-    if (KIND == SC_HP) ip_pair<true>(a0, a1, b0, b1, e, x, c, fa, fb); else ip_pair<false>(a0, a1, b0, b1, a0, x, c, fa, fb);
-  }
-  acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
-}
-template <int KIND>
-__device__ __forceinline__ void sc3_node(const Fr& a0, const Fr& a1, const Fr& b0, const Fr& b1, const Fr& e, const Fr& x, Fr* acc, Fr& fa, Fr& fb) {
-  Fr c[3];
-  if (KIND == SC_BIN) fa = bin_pair(a0, a1, e, x, c);
-  else if (KIND == SC_HP) ip_pair<true>(a0, a1, b0, b1, e, x, c, fa, fb);
-  else ip_pair<false>(a0, a1, b0, b1, a0, x, c, fa, fb);
-  acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
-}
-template <int KIND>
-__global__ void __launch_bounds__(THREADS) k_sc_round3(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
-                                                       const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x0, Fr x1, Fr x2, size_t in_size,
-                                                       size_t out_size, size_t Q, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof9) {
-  __shared__ Fr sm[3 * 32];
-  __shared__ bool is_last;
-  Fr acc[9];
-#pragma unroll
-  for (int i = 0; i < 9; ++i) acc[i] = Fr::zero();
-  // Q = (entries of the eq table) / 4 is a multiple of the warp size: whole warps stay together for the shuffle
-  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < Q; q += (size_t)gridDim.x * blockDim.x) {
-    Fr ga[2], gb[2], e2 = Fr::zero();
-#pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-      Fr fa[2], fb[2], e1 = Fr::zero();
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const size_t g = 4 * q + 2 * hlf + t;
-        Fr e = Fr::zero();
-        if (KIND != SC_IP) { e = e_in[g]; e1 = add(e1, e); }
-        sc3_pair<KIND>(a, b, g, in_size, e, x0, acc, fa[t], fb[t]);
-      }
-      sc3_node<KIND>(fa[0], fa[1], fb[0], fb[1], e1, x1, acc + 3, ga[hlf], gb[hlf]);
-      if (KIND != SC_IP) e2 = add(e2, e1);
-    }
-    Fr oa, ob;
-    sc3_node<KIND>(ga[0], ga[1], gb[0], gb[1], e2, x2, acc + 6, oa, ob);
-    if (q < out_size) { a_out[q] = oa; if (KIND != SC_BIN) b_out[q] = ob; }
-    if (KIND != SC_IP) {
-      Fr o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = __shfl_down_sync(0xffffffffu, e2.v[i], 1);
-      if (!(q & 1)) e_out[q >> 1] = add(e2, o);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    block_reduce_fr<3>(acc + 3 * r, sm);
-    if (threadIdx.x == 0)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) partials[(size_t)blockIdx.x * 9 + 3 * r + c] = acc[3 * r + c];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { __threadfence(); is_last = atomicAdd(counter, 1u) == gridDim.x - 1; }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-#pragma unroll 1
-  for (int r = 0; r < 3; ++r) {
-    Fr t[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
-    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) t[c] = add(t[c], ldcg_fr(partials + (size_t)i * 9 + 3 * r + c));
-    __syncthreads();
-    block_reduce_fr<3>(t, sm);
-    if (threadIdx.x == 0) { proof9[3 * r] = t[0]; proof9[3 * r + 1] = t[1]; proof9[3 * r + 2] = t[2]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *counter = 0;
-}
-
 // All remaining rounds (table of at most TAIL_N entries) in one CTA, entirely in shared memory: the table(s) and the eq table
 // are loaded once, every round folds them in place (compute into registers, barrier, write back, barrier: each thread owns
 // one double-pair), and the per-round coefficient sums are only reduced inside each warp; the per-warp partials of ALL rounds
@@ -558,7 +466,7 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   if (KIND != SC_BIN) { if ((rc = B0.alloc(sizeof(Fr) * half, st))) return rc; if ((rc = B1.alloc(sizeof(Fr) * half, st))) return rc; }
   size_t maxH = (half + 1) / 2; if (KIND != SC_IP && esize / 2 > maxH) maxH = esize / 2;   // HP/BIN rounds cover the whole eq table
   unsigned maxgrid = stream_grid(maxH, THREADS);
-  if ((rc = parts.alloc(sizeof(Fr) * 9 * maxgrid, st))) return rc;
+  if ((rc = parts.alloc(sizeof(Fr) * 3 * maxgrid, st))) return rc;
   Scratch counter;
   if ((rc = counter.alloc(sizeof(unsigned), st))) return rc;
   ZK_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
@@ -570,23 +478,6 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   size_t j = 0;
   for (; j < k; ++j) {
     if (cur_n <= TAIL_N) break;                           // the rest fits one CTA's shared memory
-    static const size_t fuse_max = getenv("ZKDL_SC_FUSE_MAX") ? (size_t)atol(getenv("ZKDL_SC_FUSE_MAX")) : ((size_t)1 << 17);   // tuning knob
-    if (cur_n <= fuse_max && cur_n > 4 * TAIL_N && j + 3 <= k && (KIND == SC_IP || esize >= 128)) {
-      // three rounds in one pass; the eq table (esize >= cur_n / 2 entries) bounds the loop: Q = esize / 4 threads' worth of work
-      const size_t n1 = (cur_n + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2;
-      size_t Q = KIND == SC_IP ? (cur_n + 7) / 8 : esize / 4;
-      Q = (Q + 31) / 32 * 32;
-      unsigned grid = stream_grid(Q, THREADS);
-      const double tables = KIND == SC_BIN ? 1.0 : 2.0, mulpp = KIND == SC_IP ? 5.0 : (KIND == SC_HP ? 7.0 : 6.0);
-      ZK_LAUNCH_P(st, 48.0 * (cur_n + n1 + n2) * tables + (KIND != SC_IP ? 24.0 * 1.75 * esize : 0.0), mulpp * (n1 + n2 + n3), 0.0,
-                  k_sc_round3<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], ebuf[ewhich ^ 1], host_fr(fold_host + j),
-                                                              host_fr(fold_host + j + 1), host_fr(fold_host + j + 2), cur_n, n3, Q, parts.as<Fr>(),
-                                                              counter.as<unsigned>(), proof + 3 * j));
-      ca = abuf[which]; cb = bbuf[which]; which ^= 1; cur_n = n3;
-      if (KIND != SC_IP) { ewhich ^= 1; esize /= 8; }
-      j += 2;                                             // the loop header adds the third
-      continue;
-    }
     size_t out_size = (cur_n + 1) / 2;
     bool fold_e = (KIND != SC_IP) && esize >= 2;
     size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
