@@ -28,13 +28,18 @@ typedef struct { uint32_t val[12]; } zkdl_fq_t;                /* blstrs__fp__Fp
 typedef struct { zkdl_fq_t x, y; } zkdl_g1_affine_t;           /* bls12-381.cuh:421-424 */
 typedef struct { zkdl_fq_t x, y, z; } zkdl_g1_jacobian_t;      /* bls12-381.cuh:426-430 */
 
-enum { ZKDL_OK = 0, ZKDL_ERR_DIM = 1, ZKDL_ERR_CUDA = 2, ZKDL_ERR_ARG = 3, ZKDL_ERR_NCCL = 4 };
+enum { ZKDL_OK = 0, ZKDL_ERR_DIM = 1, ZKDL_ERR_CUDA = 2, ZKDL_ERR_ARG = 3,
+       ZKDL_ERR_NCCL = 4 /* reserved: the library itself issues no collective (the multi-GPU exchanges of zkdl_b200/parallel.py go
+                            through torch.distributed / NCCL); kept so that a future in-library collective does not renumber */ };
 
 const char* zkdl_last_error(void);
 int zkdl_version(void);
 /* Pre-sizes the scratch arenas of `stream` (and of the calling thread's side streams) so that the first proof does not
  * pay for cudaMalloc.  Optional: arenas also grow on demand and are warm after the first call. */
 int zkdl_scratch_reserve(size_t bytes, void* stream);
+/* Releases every scratch arena of the current device that holds no live allocation (arenas are otherwise kept for the life
+ * of the process).  Synchronises the device.  Call between workloads of very different sizes, never from a timed region. */
+int zkdl_scratch_release_all(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t zkdl_launch_count(void);
 /* Per-kernel profiler for bench.py's roofline entries (no reference counterpart; the reference times with Timer around

@@ -61,3 +61,20 @@ def test_corrupted_files_are_rejected(proof_path, tmp_path):
     bad.write_bytes(blob[: len(blob) // 2])
     with pytest.raises(ValueError):
         proof_file.verify_file(str(bad))
+
+
+def test_subgroup_check_rejects_cofactor_points(proof_path):
+    """on-curve is not enough, BLS12-381 G1 has a cofactor.  The first abscissa with a square right-hand side gives
+    a curve point outside the prime-order subgroup (probability 1 - 1/h); real generators pass."""
+    from zkdl_b200 import capi as zk, serialize, verify
+    public, _ = serialize.loads(proof_path.read_bytes())
+    verify.verify_subgroup(zk.to_device(public["layers"][0]["generators"]))
+    x = 1
+    while True:
+        b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80
+        try:
+            pt = serialize.g1_decompress(bytes(b)); break
+        except ValueError:
+            x += 1
+    with pytest.raises(verify.VerifyError):
+        verify.verify_subgroup(zk.to_device(pt))

@@ -99,3 +99,13 @@ def test_file_round_trip_and_rejections():
     for bad in (blob[:-1], blob + b"\0", b"XKDLPRF1" + blob[8:], blob[:8] + (2).to_bytes(4, "little") + blob[12:]):
         with pytest.raises(ValueError):
             ser.loads(bad)
+
+
+def test_uncompressed_infinity_must_be_canonical():
+    """the infinity flag with non-zero payload, or compression / sort flags on an uncompressed point, are rejected."""
+    import pytest
+    from zkdl_b200 import serialize as sz
+    assert (sz.g1_from_uncompressed(bytes([0x40]) + bytes(95))[0, 24:] == 0).all()
+    for bad in (bytes([0x40]) + bytes(94) + b"\x01", bytes([0x41]) + bytes(95), bytes([0xC0]) + bytes(95), bytes([0x20]) + bytes(95)):
+        with pytest.raises(ValueError):
+            sz.g1_from_uncompressed(bad)

@@ -478,6 +478,11 @@ def scratch_reserve(nbytes):
     _check(lib().zkdl_scratch_reserve(_sz(nbytes), _stream()))
 
 
+def scratch_release_all():
+    """Frees the library's idle scratch arenas on the current device (zkdl_scratch_release_all; synchronises the device)."""
+    _check(lib().zkdl_scratch_release_all())
+
+
 def prof_enable(on=True):
     """Per-kernel profiler of the library (zkdl_prof_enable): clears the records and switches event bracketing on/off."""
     _check(lib().zkdl_prof_enable(int(bool(on))))

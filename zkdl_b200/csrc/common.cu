@@ -176,6 +176,21 @@ size_t zkdl_prof_dump(char* buf, size_t cap) {
   if (buf && cap) { size_t n = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), n); buf[n] = 0; }
   return out.size() + 1;
 }
+int zkdl_scratch_release_all(void) {
+  // Frees every scratch arena that holds no live allocation (the arenas are process-global and otherwise kept for the life
+  // of the process).  Synchronises the device first: a released block may still be in use by enqueued work.
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { zk::set_last_error("cudaDeviceSynchronize: %s", cudaGetErrorString(e)); return ZKDL_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(zk::g_arena_mu);
+  int dev = 0; cudaGetDevice(&dev);
+  for (auto it = zk::g_arenas.begin(); it != zk::g_arenas.end();) {
+    if (it->first.first == dev && it->second.stack.empty()) {
+      for (auto& b : it->second.blocks) cudaFree(b.base);
+      it = zk::g_arenas.erase(it);
+    } else ++it;
+  }
+  return ZKDL_OK;
+}
 const char* zkdl_last_error(void) { return zk::g_err; }
 int zkdl_version(void) { return 100; }
 uint64_t zkdl_launch_count(void) { return zk::g_launches.load(); }

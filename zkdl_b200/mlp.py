@@ -164,7 +164,9 @@ class MLPProver:
             old = len(getattr(self, "_streams", []))
             self._streams = getattr(self, "_streams", []) + [torch.cuda.Stream() for _ in range(streams - old)]
             self._pools = getattr(self, "_pools", []) + [ThreadPoolExecutor(max_workers=1) for _ in range(streams - old)]
-            need = 256 * max(max(L.I * L.O, 4 * B * L.O) for L in self.layers)
+            # measured peak of a slot's main arena: ~100 MB for a 2^19-activation zkReLU proof (eq / folded tables, look-up tables),
+            # ~30 MB for an opening; side-stream arenas get half.  Arenas still grow on demand if this is ever too small.
+            need = 96 * max(max(L.I * L.O, 4 * B * L.O) for L in self.layers)
 
             def reserve(slot):
                 torch.cuda.set_device(dev)

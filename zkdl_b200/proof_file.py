@@ -60,6 +60,8 @@ def verify_file(path):
     if B != 1 << clog(B):
         raise verify.VerifyError("batch is not a power of two")
     dev = [{"G": zk.to_device(L["generators"]), "com": zk.to_device(L["commitment"])} for L in public["layers"]]
+    for i_, D in enumerate(dev):                                      # on-curve is checked by the parser; subgroup membership here
+        verify.verify_subgroup(D["G"], f"layer {i_} generators"); verify.verify_subgroup(D["com"], f"layer {i_} commitment")
     summary = []
     for t in tasks:
         L, D = public["layers"][t["layer"]], dev[t["layer"]]
@@ -80,6 +82,7 @@ def verify_file(path):
             if t["fr"].shape[0] != 3 * want[1] + 4 or t["g1"] is None or t["g1"].shape[0] != 3 * clog(ng) + 2:
                 raise verify.VerifyError(f"fc {t['layer']}: wrong number of proof elements")
             g1 = zk.to_device(t["g1"])
+            verify.verify_subgroup(g1, f"fc {t['layer']} proof points")
             info = verify.verify_zkfc(fr, g1, D["G"], B, L["I"], L["O"], u_bs, u_in, u_out)
             u = np.concatenate([u_out.reshape(-1, 8), u_in.reshape(-1, 8)])
             klo = (D["G"].shape[0] - 1).bit_length()

@@ -137,7 +137,11 @@ def g1_from_uncompressed(buf, check=True):
     aff = []
     for i in range(0, len(buf), 96):
         b = buf[i:i + 96]
+        if b[0] & 0xA0:
+            raise ValueError("compression / sort flags set in an uncompressed point")
         if b[0] & 0x40:
+            if (b[0] & 0x3F) or any(b[1:]):
+                raise ValueError("malformed point at infinity")
             aff.append(None)
             continue
         x, y = int.from_bytes(b[:48], "big"), int.from_bytes(b[48:], "big")

@@ -128,6 +128,16 @@ def verify_opening(G, com_eval, open_proof, open_ret, u_lo, gens_table=None):
     return s_final * RINV % P                                          # the opened evaluation W~(u)
 
 
+def verify_subgroup(points, what="point"):
+    """BLS12-381 G1 has cofactor 0x396c8c005555e1568c00aaab0000aaab: an on-curve point need not lie in the prime-order subgroup
+    the protocol lives in.  [r] P must be the point at infinity for every generator, commitment and proof element."""
+    if points is None or points.shape[0] == 0:
+        return
+    r = zk.to_device(np.repeat(int_to_limbs([P]), points.shape[0], axis=0))
+    z = zk.to_host(zk.g1_mul(points, r))[:, 24:]
+    _req(not z.any(), f"{what}: not in the prime-order subgroup")
+
+
 def verify_commitment_eval(com, com_eval, u_hi):
     """com(u_hi) (proof_g1[0]) against the PUBLIC row commitments: sum_r eq(u_hi, r) com[r]  (g1-tensor.cu:463-491)."""
     w = [1]
