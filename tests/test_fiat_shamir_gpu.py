@@ -76,3 +76,26 @@ def test_fs_tampering_is_rejected(setup):
     pub = copy.deepcopy(public); pub[2]["commitment"][0] = public[2]["commitment"][1]
     rejected(pub, proofs)                                # the root, hence every challenge, depends on the public commitments
     rejected(public, proofs[:-1])
+
+
+def test_fs_proof_file_roundtrip(setup, tmp_path):
+    """prove --fiat-shamir -> file -> verify from the file alone: the file holds no challenges (version 2), the verifier
+    re-derives them; a flipped proof limb or a swapped public commitment is rejected."""
+    zk, fs, P, public, proofs = setup
+    from zkdl_b200 import proof_file, serialize, verify
+    path = tmp_path / "fs.zkp"
+    n = proof_file.export_fs(P, public, proofs, str(path))
+    assert n == path.stat().st_size
+    s = proof_file.verify_file(str(path))
+    assert [(k, i) for k, i, _ in s] == [(p[0], p[1]) for p in proofs]
+    pub, tasks = serialize.loads(path.read_bytes())
+    assert pub["fiat_shamir"] and all(t["challenges"] == [] for t in tasks)
+    bad = tmp_path / "bad.zkp"
+    t = copy.deepcopy(tasks); t[0]["fr"][2, 0] ^= 1
+    bad.write_bytes(serialize.dumps(pub, t, fiat_shamir=True))
+    with pytest.raises(verify.VerifyError):
+        proof_file.verify_file(str(bad))
+    p2 = copy.deepcopy(pub); p2["layers"][1]["commitment"][0] = pub["layers"][1]["commitment"][1]
+    bad.write_bytes(serialize.dumps(p2, tasks, fiat_shamir=True))
+    with pytest.raises(verify.VerifyError):
+        proof_file.verify_file(str(bad))

@@ -70,11 +70,15 @@ class Transcript:
 
 def public_root(layers, batch):
     """Digest of the public part: batch, padded shapes, generators and weight commitments (normalised Jacobian limbs)."""
+    def canon(points):                                       # infinity (z = 0) has many limb images: hash it as all zeros
+        a = np.array(points, dtype=np.uint32).reshape(-1, 36)
+        a[(a[:, 24:] == 0).all(axis=1)] = 0
+        return a.astype("<u4").tobytes()
     h = hashlib.sha256(DOMAIN + b"/root" + int(batch).to_bytes(4, "little"))
     for L in layers:
         h.update(np.array([L["in_dim"], L["out_dim"], L["I"], L["O"]], dtype="<u4").tobytes())
-        h.update(np.ascontiguousarray(L["generators"], dtype=np.uint32).astype("<u4").tobytes())
-        h.update(np.ascontiguousarray(L["commitment"], dtype=np.uint32).astype("<u4").tobytes())
+        h.update(canon(L["generators"]))
+        h.update(canon(L["commitment"]))
     return h.digest()
 
 

@@ -26,6 +26,17 @@ import numpy as np
 from . import serialize
 
 
+def export_fs(P, public_layers, proofs, path):
+    """Fiat-Shamir mode: public_layers, proofs = fiat_shamir.prove(P).  The file carries no challenges."""
+    from . import capi as zk
+    tasks = [{"kind": p[0], "layer": p[1], "challenges": [], "fr": zk.to_host(p[2]),
+              "g1": zk.to_host(zk.g1_normalize(p[3])) if p[0] == "fc" else None} for p in proofs]
+    blob = serialize.dumps({"batch": P.B, "layers": public_layers}, tasks, fiat_shamir=True)
+    with open(path, "wb") as f:
+        f.write(blob)
+    return len(blob)
+
+
 def export(P, proof, path):
     """P: MLPProver after forward() and prove(); proof: what prove() returned (whole tasks only)."""
     from . import capi as zk
@@ -62,6 +73,16 @@ def verify_file(path):
     dev = [{"G": zk.to_device(L["generators"]), "com": zk.to_device(L["commitment"])} for L in public["layers"]]
     for i_, D in enumerate(dev):                                      # on-curve is checked by the parser; subgroup membership here
         verify.verify_subgroup(D["G"], f"layer {i_} generators"); verify.verify_subgroup(D["com"], f"layer {i_} commitment")
+    if public.get("fiat_shamir"):                                     # challenges are re-derived from the transcript, not read
+        from . import fiat_shamir
+        proofs = []
+        for t in tasks:
+            g1 = zk.to_device(t["g1"]) if t["g1"] is not None else None
+            if g1 is not None:
+                verify.verify_subgroup(g1, f"fc {t['layer']} proof points")
+            proofs.append((t["kind"], t["layer"], zk.to_device(t["fr"])) + ((g1,) if g1 is not None else ()))
+        fiat_shamir.verify_all(public["layers"], B, proofs)
+        return [(t["kind"], t["layer"], None) for t in tasks]
     summary = []
     for t in tasks:
         L, D = public["layers"][t["layer"]], dev[t["layer"]]
@@ -116,6 +137,7 @@ def main(argv=None):
     sub = ap.add_subparsers(dest="cmd", required=True)
     pp = sub.add_parser("prove"); pp.add_argument("--out", required=True); pp.add_argument("--model"); pp.add_argument("--input")
     pp.add_argument("--seed", type=int, default=0); pp.add_argument("--batch", type=int, default=256)
+    pp.add_argument("--fiat-shamir", action="store_true", help="derive every challenge from a SHA-256 transcript (zkdl_b200/fiat_shamir.py) instead of seeded random_vec streams")
     pv = sub.add_parser("verify"); pv.add_argument("file")
     a = ap.parse_args(argv)
     import torch
@@ -130,11 +152,19 @@ def main(argv=None):
             ws, x = mlp.synthetic_mlp(mlp.demo_layer_dims(), a.batch, seed=0)
         P = mlp.MLPProver(ws, gen_seed=a.seed + 1)
         P.forward(x)
-        P.prove(seed=a.seed)                                             # warm-up (scratch arenas)
-        torch.cuda.synchronize(); t0 = time.time()
-        proof = P.prove(seed=a.seed)
-        torch.cuda.synchronize(); dt = time.time() - t0
-        n = export(P, proof, a.out)
+        if a.fiat_shamir:
+            from . import fiat_shamir
+            fiat_shamir.prove(P)                                         # warm-up
+            torch.cuda.synchronize(); t0 = time.time()
+            pub, proof = fiat_shamir.prove(P)
+            torch.cuda.synchronize(); dt = time.time() - t0
+            n = export_fs(P, pub, proof, a.out)
+        else:
+            P.prove(seed=a.seed)                                         # warm-up (scratch arenas)
+            torch.cuda.synchronize(); t0 = time.time()
+            proof = P.prove(seed=a.seed)
+            torch.cuda.synchronize(); dt = time.time() - t0
+            n = export(P, proof, a.out)
         print(f"Total number of parameters: {P.n_params}")
         print(f"Proof time: {dt / x.shape[0]} seconds per data point.  {len(proof)} layer proofs, {n} bytes -> {a.out}")
     else:

@@ -156,11 +156,12 @@ def _u32(*v):
     return struct.pack("<%dI" % len(v), *v)
 
 
-def dumps(public, tasks):
+def dumps(public, tasks, fiat_shamir=False):
     """public: [{in_dim, out_dim, I, O, generators [n,36] normalised, commitment [m,36] normalised}] per layer;
     tasks: [{kind: "fc"|"relu", layer, challenges: [[k,8] limbs ...], fr: [r,8] limbs, g1: [s,36] normalised or None}]
-    in proving order; batch is stored in the header."""
-    out = [MAGIC, _u32(1, len(public["layers"]), public["batch"])]
+    in proving order; batch is stored in the header.  Version 1 = injected challenges (stored per task); version 2 =
+    Fiat-Shamir mode (zkdl_b200/fiat_shamir.py): same layout, every task's challenge list is empty - the verifier derives them."""
+    out = [MAGIC, _u32(2 if fiat_shamir else 1, len(public["layers"]), public["batch"])]
     for L in public["layers"]:
         out.append(_u32(L["in_dim"], L["out_dim"], L["I"], L["O"], len(L["generators"]), len(L["commitment"])))
         out.append(g1_uncompressed(L["generators"]))
@@ -199,7 +200,7 @@ def loads(buf):
     if r.take(8) != MAGIC:
         raise ValueError("not a zkdl_b200 proof file")
     version, nl, batch = r.u32(3)
-    if version != 1:
+    if version not in (1, 2):
         raise ValueError("unsupported proof file version %d" % version)
     layers = []
     for _ in range(nl):
@@ -218,4 +219,6 @@ def loads(buf):
                       "g1": g1_decompress(r.take(48 * ng1)) if ng1 else None})
     if r.o != len(buf):
         raise ValueError("trailing bytes after the last task")
-    return {"batch": batch, "layers": layers}, tasks
+    if version == 2 and any(t["challenges"] for t in tasks):
+        raise ValueError("a Fiat-Shamir proof file must not carry challenges")
+    return {"batch": batch, "layers": layers, "fiat_shamir": version == 2}, tasks
