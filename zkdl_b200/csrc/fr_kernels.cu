@@ -241,43 +241,38 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__
   for (size_t i = tid; i < in_size; i += blockDim.x) { sa[i] = a_g[i]; if (KIND != SC_BIN) sb[i] = b_g[i]; }
   if (KIND != SC_IP) for (size_t i = tid; i < esize; i += blockDim.x) se[i] = e_g[i];
   __syncthreads();
-  const size_t in0 = in_size, es0 = esize;
+  const size_t in0 = in_size;
   for (int j = 0; j < rounds; ++j) {
-    const size_t out_size = (in_size + 1) / 2;
+    const size_t pairs = (in_size + 1) / 2;                       // <= 2 * TAIL_THREADS in the first round, <= TAIL_THREADS afterwards
     const bool fold_e = (KIND != SC_IP) && esize >= 2;
-    const size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;     // <= TAIL_THREADS: one double-pair per thread
-    const int nact = (int)((H + 31) / 32);
-    Fr ao[2], bo[2], eo;
-    bool wr[2] = {false, false};
+    const int nact = (int)(((pairs < (size_t)TAIL_THREADS ? pairs : (size_t)TAIL_THREADS) + 31) / 32);
+    Fr ao[2], bo[2], eo[2];
+    bool wr[2] = {false, false}, wre[2] = {false, false};
     if (warp < nact) {
       Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
-      const size_t h = tid;
-      if (h < H) {
-        const Fr x = sx[j];
-        Fr e0, e1;
-        if (KIND != SC_IP) {
-          e0 = se[2 * h];
-          if (fold_e) { e1 = se[2 * h + 1]; eo = add(e0, e1); } else e1 = Fr::zero();
-        }
+      const Fr x = sx[j];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const size_t g = 2 * h + t;
-          if (g >= out_size) break;
-          const size_t g0 = 2 * g, g1 = 2 * g + 1;
-          Fr a0 = g0 < in_size ? sa[g0] : Fr::zero();
-          Fr a1 = g1 < in_size ? sa[g1] : Fr::zero();
-          Fr c[3];
-          if (KIND == SC_BIN) {
-            ao[t] = bin_pair(a0, a1, t ? e1 : e0, x, c);
-          } else {
-            Fr b0 = g0 < in_size ? sb[g0] : Fr::zero();
-            Fr b1 = g1 < in_size ? sb[g1] : Fr::zero();
-            if (KIND == SC_HP) ip_pair<true>(a0, a1, b0, b1, t ? e1 : e0, x, c, ao[t], bo[t]);
-            else ip_pair<false>(a0, a1, b0, b1, a0, x, c, ao[t], bo[t]);
-          }
-          wr[t] = true;
-          acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
+      for (int it = 0; it < 2; ++it) {                            // one pair per thread (two only in a first round of > 512 pairs)
+        const size_t g = (size_t)tid + (size_t)it * TAIL_THREADS;
+        if (g >= pairs) break;
+        const size_t g0 = 2 * g, g1 = 2 * g + 1;
+        Fr a0 = sa[g0];
+        Fr a1 = g1 < in_size ? sa[g1] : Fr::zero();
+        Fr e = Fr::zero(), c[3];
+        if (KIND != SC_IP) {
+          e = se[g];
+          if (fold_e && !(g & 1)) { eo[it] = add(e, se[g + 1]); wre[it] = true; }     // next round's weight of pair g / 2
         }
+        if (KIND == SC_BIN) {
+          ao[it] = bin_pair(a0, a1, e, x, c);
+        } else {
+          Fr b0 = sb[g0];
+          Fr b1 = g1 < in_size ? sb[g1] : Fr::zero();
+          if (KIND == SC_HP) ip_pair<true>(a0, a1, b0, b1, e, x, c, ao[it], bo[it]);
+          else ip_pair<false>(a0, a1, b0, b1, a0, x, c, ao[it], bo[it]);
+        }
+        wr[it] = true;
+        acc[0] = add(acc[0], c[0]); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]);
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -292,22 +287,24 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__
       if (lane == 0) { Fr* r = red + ((size_t)j * TAIL_WARPS + warp) * 3; r[0] = acc[0]; r[1] = acc[1]; r[2] = acc[2]; }
     }
     __syncthreads();                                                // every read of this round's tables is done
-    if (warp < nact && (size_t)tid < H) {
+    if (warp < nact) {
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (wr[t]) { sa[2 * tid + t] = ao[t]; if (KIND != SC_BIN) sb[2 * tid + t] = bo[t]; }
-      if (fold_e) se[tid] = eo;
+      for (int it = 0; it < 2; ++it)
+        if (wr[it]) {
+          const size_t g = (size_t)tid + (size_t)it * TAIL_THREADS;
+          sa[g] = ao[it]; if (KIND != SC_BIN) sb[g] = bo[it];
+          if (wre[it]) se[g >> 1] = eo[it];
+        }
     }
     __syncthreads();
-    in_size = out_size; esize = esize >= 2 ? esize / 2 : 1;
+    in_size = pairs; esize = esize >= 2 ? esize / 2 : 1;
   }
   if (tid < 3 * rounds) {                                           // the deferred cross-warp sums, all rounds in parallel
     const int j = tid / 3, c = tid % 3;
-    size_t n = in0, es = es0;
-    for (int r = 0; r < j; ++r) { n = (n + 1) / 2; es = es >= 2 ? es / 2 : 1; }
-    const size_t out_size = (n + 1) / 2;
-    const size_t H = ((KIND != SC_IP) && es >= 2) ? es / 2 : (out_size + 1) / 2;
-    const int nact = (int)((H + 31) / 32);
+    size_t n = in0;
+    for (int r = 0; r < j; ++r) n = (n + 1) / 2;
+    const size_t pairs = (n + 1) / 2;
+    const int nact = (int)(((pairs < (size_t)TAIL_THREADS ? pairs : (size_t)TAIL_THREADS) + 31) / 32);
     Fr sum = red[((size_t)j * TAIL_WARPS) * 3 + c];
     for (int w = 1; w < nact; ++w) sum = add(sum, red[((size_t)j * TAIL_WARPS + w) * 3 + c]);
     proof[3 * j + c] = sum;

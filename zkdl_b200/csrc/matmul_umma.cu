@@ -6,14 +6,15 @@
 // s32 accumulators (every partial sum < 2^31 for K <= 16384), recombined exactly in the epilogue, reduced mod p and
 // written as Montgomery Fr: bit-identical to the reference's Montgomery dot products.
 //
-// One CTA = one 128 x 64 output tile, 128 threads:
+// One CTA = one 128 x 64 output tile, 512 threads:
 //   warp 0 / lane 0  TMA producer: per 128-byte k-block five 2-D tile loads (3 A planes 128 x 128 B, 2 W^T planes 64 x 128 B,
 //                    SWIZZLE_128B) into a 3-stage shared-memory ring, completion on the stage's `full` mbarrier
 //   warp 1 / lane 0  MMA issuer: 4 k-steps (UMMA_K = 32 bytes) x 6 tcgen05.mma.kind::i8 (M 128, N 64) per k-block into four
 //                    64-column TMEM accumulators (u8 x u8, u8 x s8, s8 x u8, s8 x s8 instruction descriptors),
 //                    tcgen05.commit frees the stage / signals the epilogue
-//   warps 0-3        epilogue: tcgen05.ld 32x32b (warp w owns TMEM lanes 32w..32w+31 = output rows), recombination,
-//                    to_mont, 32-byte stores
+//   warps 0-15       epilogue: tcgen05.ld 32x32b (warp w reads TMEM lanes 32 (w % 4) .. +31 = output rows, columns
+//                    16 (w / 4) .. +15), recombination, to_mont, 32-byte stores.  (With 4 warps the epilogue - 64 dependent
+//                    Montgomery products per thread, one warp per scheduler - took 4x longer than the whole main loop.)
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -27,6 +28,8 @@ constexpr int BM = 128, BN = 64, BK = 128, STAGES = 3, NA = 3, NW = 2;
 constexpr int A_BYTES = BM * BK, W_BYTES = BN * BK;                  // one plane of a stage
 constexpr int STAGE_BYTES = NA * A_BYTES + NW * W_BYTES;             // 64 KiB
 constexpr int TMEM_COLS = 256;                                       // 4 accumulators x 64 columns
+constexpr int NTHREADS = 512;                                        // 16 warps: 4 lane quarters x 4 column chunks of 16 in the epilogue
+static_assert(BN == 16 * (NTHREADS / 128), "one 16-column chunk per epilogue warp");
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + TMEM slot */;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -78,7 +81,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
                : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(128, 1) k_umma_matmul(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+__global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                                                         Fr* __restrict__ C, uint32_t M, uint32_t K, uint32_t N, const uint32_t* __restrict__ info) {
   if (!info[4]) return;                                               // routed elsewhere (operands not small enough)
   extern __shared__ uint8_t umma_smem_raw[];
@@ -147,10 +150,10 @@ __global__ void __launch_bounds__(128, 1) k_umma_matmul(const __grid_constant__ 
   // ---- epilogue: TMEM lane = output row, column = output column
   mbar_wait(accum, 0);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const size_t grow = (size_t)row0 + warp * 32 + lane;
-  const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
-  for (int c = 0; c < BN; c += 16) {
+  const int quarter = warp & 3, c = (warp >> 2) * 16;                 // a warp may only read the TMEM lanes 32 (warp % 4) .. +31
+  const size_t grow = (size_t)row0 + quarter * 32 + lane;
+  const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+  {
     uint32_t acc[4][16];
 #pragma unroll
     for (int s = 0; s < 4; ++s) tmem_ld16(lane_base + s * BN + c, acc[s]);
@@ -213,7 +216,7 @@ int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, si
     attr_set = true;
   }
   dim3 grid((unsigned)(N / umma::BN), (unsigned)(M / umma::BM));
-  ZK_LAUNCH(umma::k_umma_matmul<<<grid, 128, umma::SMEM_BYTES, st>>>(mapA, mapW, C, (uint32_t)M, (uint32_t)K, (uint32_t)N, info));
+  ZK_LAUNCH(umma::k_umma_matmul<<<grid, umma::NTHREADS, umma::SMEM_BYTES, st>>>(mapA, mapW, C, (uint32_t)M, (uint32_t)K, (uint32_t)N, info));
   return ZK_OK;
 }
 
