@@ -246,8 +246,11 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__
     const size_t pairs = (in_size + 1) / 2;                       // <= 2 * TAIL_THREADS in the first round, <= TAIL_THREADS afterwards
     const bool fold_e = (KIND != SC_IP) && esize >= 2;
     const int nact = (int)(((pairs < (size_t)TAIL_THREADS ? pairs : (size_t)TAIL_THREADS) + 31) / 32);
-    Fr ao[2], bo[2], eo[2];
-    bool wr[2] = {false, false}, wre[2] = {false, false};
+    Fr ao[2], bo[2], eo;
+    bool wr[2] = {false, false};
+    // the WHOLE eq table is folded every round (entries beyond the table's pairs feed later rounds of a ragged table)
+    const bool wre = fold_e && (size_t)tid < esize / 2;
+    if (wre) eo = add(se[2 * tid], se[2 * tid + 1]);
     if (warp < nact) {
       Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
       const Fr x = sx[j];
@@ -261,7 +264,6 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__
         Fr e = Fr::zero(), c[3];
         if (KIND != SC_IP) {
           e = se[g];
-          if (fold_e && !(g & 1)) { eo[it] = add(e, se[g + 1]); wre[it] = true; }     // next round's weight of pair g / 2
         }
         if (KIND == SC_BIN) {
           ao[it] = bin_pair(a0, a1, e, x, c);
@@ -293,9 +295,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_sc_tail(const Fr* __restrict__
         if (wr[it]) {
           const size_t g = (size_t)tid + (size_t)it * TAIL_THREADS;
           sa[g] = ao[it]; if (KIND != SC_BIN) sb[g] = bo[it];
-          if (wre[it]) se[g >> 1] = eo[it];
         }
     }
+    if (wre) se[tid] = eo;
     __syncthreads();
     in_size = pairs; esize = esize >= 2 ? esize / 2 : 1;
   }
