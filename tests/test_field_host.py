@@ -88,6 +88,14 @@ def test_sumcheck_pair_math(hs):
     assert np.array_equal(c[0::3], orc.fr_mul(e, orc.fr_sub(orc.fr_mul(a0, a0), a0)))
     assert np.array_equal(c[1::3], orc.fr_mul(e, orc.fr_sub(orc.fr_mul(orc.fr_add(a0, a0), da), da)))
     assert np.array_equal(c[2::3], orc.fr_mul(e, orc.fr_mul(da, da)))
+    # the 4-product form used when c0 is derived from the running claim: same c1, c2 and fold; and the derivation itself:
+    # for ONE pair the round's claim is c0 + u (c1 + c2) for any u, so c0 == claim - u (c1 + c2)
+    c12 = np.zeros((3 * n, 8), np.uint32); ao2 = np.zeros_like(a0)
+    hs.hs_bin_pair_c12(p(a0), p(a1), p(e), p(x), p(c12), p(ao2), C.c_size_t(n))
+    assert np.array_equal(c12[1::3], c[1::3]) and np.array_equal(c12[2::3], c[2::3]) and np.array_equal(ao2, ao)
+    u = rand(n - 5, 8)
+    claim = orc.fr_add(c[0::3], orc.fr_mul(u, orc.fr_add(c[1::3], c[2::3])))
+    assert np.array_equal(orc.fr_sub(claim, orc.fr_mul(u, orc.fr_add(c12[1::3], c12[2::3]))), c[0::3])
 
 
 def test_quantise_and_relu_device_functions(hs):

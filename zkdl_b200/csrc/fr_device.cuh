@@ -38,6 +38,17 @@ ZK_HD Fr bin_pair(const Fr& a0, const Fr& a1, const Fr& e, const Fr& x, Fr* c) {
   return add(a0, mul(x, d));
 }
 
+// The same pair without c0 (4 products instead of 6): every round's verifier identity  claim_j = c0 + u_j (c1 + c2)  fixes c0
+// once the running claim is known, so only c1 and c2 have to be SUMMED over the table; the kernel that finishes a round
+// derives c0 = claim_j - u_j (c1 + c2) and the next claim c0 + v_j (c1 + v_j c2).  Exact field identities: same proof elements.
+ZK_HD Fr bin_pair_c12(const Fr& a0, const Fr& a1, const Fr& e, const Fr& x, Fr* c) {
+  Fr d = sub(a1, a0);
+  Fr ed = mul(e, d);
+  c[1] = mul(ed, sub(dbl(a0), Fr::one()));
+  c[2] = mul(ed, d);
+  return add(a0, mul(x, d));
+}
+
 // ---- sums of (small integer) x (field element): an unsigned 320-bit accumulator, reduced once at the end.
 // Used to fold a table of quantised weights against an eq table without a Montgomery product per entry:
 // sum_i w_i * E_i mod p with |w_i| < 2^32 is the same field element as the Montgomery sum of products mont(w_i) (x) E_i.

@@ -143,7 +143,7 @@ enum { SC_IP = 0, SC_HP = 1, SC_BIN = 2 };
 
 // One round over the pairs handled by this thread; accumulates the three coefficient sums into acc[3].
 // h indexes double-pairs so that the eq table for the next round (E'[h] = E[2h] + E[2h+1]) is produced in the same pass.
-template <int KIND>
+template <int KIND, bool DERIVE = false>
 __device__ __forceinline__ void sc_round_items(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
                                                const Fr* __restrict__ e_in, Fr* __restrict__ e_out, const Fr& x, size_t in_size, size_t out_size,
                                                size_t H, size_t h0, size_t hstride, Fr* acc) {
@@ -163,6 +163,7 @@ __device__ __forceinline__ void sc_round_items(const Fr* __restrict__ a, const F
       Fr c[3];
       if (KIND == SC_BIN) {
         const Fr& e = t ? e1 : e0;
+        if (DERIVE) { a_out[g] = bin_pair_c12(a0, a1, e, x, c); acc[1] = add(acc[1], c[1]); acc[2] = add(acc[2], c[2]); continue; }
         a_out[g] = bin_pair(a0, a1, e, x, c);
       } else {
         Fr b0 = g0 < in_size ? b[g0] : Fr::zero();
@@ -187,15 +188,18 @@ __device__ __forceinline__ Fr ldcg_fr(const Fr* p) {          // L2 load (other 
 }
 // One sumcheck round over the whole table.  Per-CTA partial sums go to `partials`; the last CTA to finish (ticket from
 // `counter`, which it resets) adds them up and writes the round's three proof elements: no separate reduction launch.
-template <int KIND>
+// DERIVE (binary sumcheck, every round after the first): only c1 and c2 are summed; c0 follows from the running claim kept in
+// `claim` (device), which every round's last CTA advances: claim_{j+1} = c0 + x (c1 + x c2), x = this round's fold challenge.
+template <int KIND, bool DERIVE>
 __global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
                                                       const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x, size_t in_size, size_t out_size,
-                                                      size_t H, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof3) {
+                                                      size_t H, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof3,
+                                                      Fr uj, Fr* __restrict__ claim) {
   __shared__ Fr sm[3 * 32];
   __shared__ bool is_last;
   Fr acc[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
-  sc_round_items<KIND>(a, b, a_out, b_out, e_in, e_out, x, in_size, out_size, H,
-                       blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, acc);
+  sc_round_items<KIND, DERIVE>(a, b, a_out, b_out, e_in, e_out, x, in_size, out_size, H,
+                               blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, acc);
   block_reduce_fr<3>(acc, sm);
   if (threadIdx.x == 0) {
     partials[blockIdx.x * 3 + 0] = acc[0]; partials[blockIdx.x * 3 + 1] = acc[1]; partials[blockIdx.x * 3 + 2] = acc[2];
@@ -213,7 +217,13 @@ __global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, 
   }
   __syncthreads();
   block_reduce_fr<3>(acc, sm);
-  if (threadIdx.x == 0) { proof3[0] = acc[0]; proof3[1] = acc[1]; proof3[2] = acc[2]; *counter = 0; }
+  if (threadIdx.x == 0) {
+    if (KIND == SC_BIN && claim) {
+      if (DERIVE) acc[0] = sub(*claim, mul(uj, add(acc[1], acc[2])));           // claim_j = c0 + u_j (c1 + c2)
+      *claim = add(acc[0], mul(x, add(acc[1], mul(x, acc[2]))));                // g_j(x)
+    }
+    proof3[0] = acc[0]; proof3[1] = acc[1]; proof3[2] = acc[2]; *counter = 0;
+  }
 }
 
 // All remaining rounds (table of at most TAIL_N entries) in one CTA, entirely in shared memory: the table(s) and the eq table
@@ -438,8 +448,11 @@ static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k,
   return ZK_OK;
 }
 
+// claim_in (binary sumcheck only): the running claim on the device when these rounds continue a sumcheck whose first rounds
+// were done elsewhere (relu_packed.cu); nullptr = a sumcheck of its own, whose first round establishes the claim.
 template <int KIND>
-static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, Fr* proof, cudaStream_t st) {
+static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, Fr* proof, cudaStream_t st,
+                           const Fr* claim_in = nullptr) {
   // fold challenges: IP folds with u, HP/BIN fold with v and weight with eq(u[1:])
   const zkdl_fr_t* fold_host = (KIND == SC_IP) ? u_host : v_host;
   int rc;
@@ -466,9 +479,14 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   size_t maxH = (half + 1) / 2; if (KIND != SC_IP && esize / 2 > maxH) maxH = esize / 2;   // HP/BIN rounds cover the whole eq table
   unsigned maxgrid = stream_grid(maxH, THREADS);
   if ((rc = parts.alloc(sizeof(Fr) * 3 * maxgrid, st))) return rc;
-  Scratch counter;
+  Scratch counter, claim;
   if ((rc = counter.alloc(sizeof(unsigned), st))) return rc;
   ZK_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned), st));
+  bool have_claim = false;
+  if (KIND == SC_BIN) {
+    if ((rc = claim.alloc(sizeof(Fr), st))) return rc;
+    if (claim_in) { ZK_CUDA(cudaMemcpyAsync(claim.p, claim_in, sizeof(Fr), cudaMemcpyDeviceToDevice, st)); have_claim = true; }
+  }
 
   const Fr *ca = a, *cb = b; size_t cur_n = n;
   Fr *abuf[2] = {A0.as<Fr>(), A1.as<Fr>()}, *bbuf[2] = {B0.as<Fr>(), B1.as<Fr>()};
@@ -482,10 +500,21 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
     size_t H = fold_e ? esize / 2 : (out_size + 1) / 2;
     unsigned grid = stream_grid(H, THREADS);
     // 48 n B per table per round (+ the eq table: 32 B read per two pairs, 16 B written); 5 / 7 / 6 products per pair
-    const double tables = KIND == SC_BIN ? 1.0 : 2.0, mulpp = KIND == SC_IP ? 5.0 : (KIND == SC_HP ? 7.0 : 6.0);
-    ZK_LAUNCH_P(st, 48.0 * cur_n * tables + (KIND != SC_IP ? 24.0 * esize : 0.0), mulpp * out_size, 0.0,
-                k_sc_round<KIND><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
-                                                           host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j));
+    // (binary rounds that derive c0 from the running claim: 4)
+    const bool derive = KIND == SC_BIN && have_claim;
+    const double tables = KIND == SC_BIN ? 1.0 : 2.0, mulpp = KIND == SC_IP ? 5.0 : (KIND == SC_HP ? 7.0 : (derive ? 4.0 : 6.0));
+    const Fr uj = KIND == SC_BIN ? host_fr(u_host + j) : Fr::zero();
+    if (derive)
+      ZK_LAUNCH_P(st, 48.0 * cur_n * tables + 24.0 * esize, mulpp * out_size, 0.0,
+                  k_sc_round<KIND, true><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
+                                                                   host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j,
+                                                                   uj, claim.as<Fr>()));
+    else
+      ZK_LAUNCH_P(st, 48.0 * cur_n * tables + (KIND != SC_IP ? 24.0 * esize : 0.0), mulpp * out_size, 0.0,
+                  k_sc_round<KIND, false><<<grid, THREADS, 0, st>>>(ca, cb, abuf[which], bbuf[which], ebuf[ewhich], fold_e ? ebuf[ewhich ^ 1] : nullptr,
+                                                                    host_fr(fold_host + j), cur_n, out_size, H, parts.as<Fr>(), counter.as<unsigned>(), proof + 3 * j,
+                                                                    uj, KIND == SC_BIN ? claim.as<Fr>() : nullptr));
+    have_claim = KIND == SC_BIN;                           // a full first round has established it
     ca = abuf[which]; cb = bbuf[which]; which ^= 1; cur_n = out_size;
     if (fold_e) { ewhich ^= 1; esize /= 2; }
   }
@@ -503,6 +532,10 @@ static int sumcheck_driver(const Fr* a, const Fr* b, size_t n, const zkdl_fr_t* 
   return ZK_OK;
 }
 
+// exposed to relu_packed.cu: the remaining rounds of a binary sumcheck whose running claim is already on the device
+int bin_sumcheck_continue(const Fr* a, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, const Fr* claim_dev, Fr* proof, cudaStream_t st) {
+  return sumcheck_driver<SC_BIN>(a, nullptr, n, u_host, v_host, k, proof, st, claim_dev);
+}
 // exposed to msm.cu / prove.cu
 int fr_partial_me_dev(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k, size_t w, Fr* out, cudaStream_t st) {
   return fold_driver(a, n, u_host, k, w, out, st);

@@ -24,6 +24,7 @@
 namespace zk {
 
 int build_eq_table(const Fr* q_dev, const zkdl_fr_t* q_host, int t, int rev, Fr* E, cudaStream_t st);
+int bin_sumcheck_continue(const Fr* a, size_t n, const zkdl_fr_t* u_host, const zkdl_fr_t* v_host, size_t k, const Fr* claim_dev, Fr* proof, cudaStream_t st);
 
 template <int Q> struct PackLayout {
   static constexpr int LOGQ = Q == 32 ? 5 : 4;
@@ -125,21 +126,22 @@ __global__ void __launch_bounds__(512) k_bin_packed3(const T* __restrict__ packe
     uint32_t diff = (w ^ (w >> 1));                       // bit 2t set <=> cells 2t, 2t+1 differ
 #pragma unroll 4
     for (int t = 0; t < PL::N0; ++t) if ((diff >> (2 * t)) & 1u) s0 = add(s0, E0[t]);
+    // only c1 and c2 of rounds 1 and 2 are summed: c0 follows from the running claim (k_bin_packed_finish), see bin_pair_c12
     Fr s1[3] = {Fr::zero(), Fr::zero(), Fr::zero()}, s2[3] = {Fr::zero(), Fr::zero(), Fr::zero()};
 #pragma unroll 2
     for (int t = 0; t < PL::N1; ++t) {
       const Fr* e = L1 + (t * 16 + ((w >> (4 * t)) & 15u)) * 3;
-      s1[0] = add(s1[0], e[0]); s1[1] = add(s1[1], e[1]); s1[2] = add(s1[2], e[2]);
+      s1[1] = add(s1[1], e[1]); s1[2] = add(s1[2], e[2]);
     }
 #pragma unroll
     for (int t = 0; t < PL::N2; ++t) {
       uint32_t byte = (w >> (8 * t)) & 255u;
       const Fr* e = L2 + (t * 256 + byte) * 3;
-      s2[0] = add(s2[0], e[0]); s2[1] = add(s2[1], e[1]); s2[2] = add(s2[2], e[2]);
+      s2[1] = add(s2[1], e[1]); s2[2] = add(s2[2], e[2]);
     }
     acc[0] = add(acc[0], mul(eh, s0));
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { acc[1 + k] = add(acc[1 + k], mul(eh, s1[k])); acc[4 + k] = add(acc[4 + k], mul(eh, s2[k])); }
+    for (int k = 1; k < 3; ++k) { acc[1 + k] = add(acc[1 + k], mul(eh, s1[k])); acc[4 + k] = add(acc[4 + k], mul(eh, s2[k])); }
   }
   __shared__ Fr red[3 * 32];
   block_reduce_fr<3>(acc, red);
@@ -172,20 +174,20 @@ __global__ void __launch_bounds__(256, 2) k_bin_r34(const T* __restrict__ packed
     uint32_t w = packed[i];
     Fr eh = e_hi[i];
     const Fr* e = L3 + (size_t)(w & 0xffffu) * 3;
-    Fr s3[3] = {ldg_fr(e), ldg_fr(e + 1), ldg_fr(e + 2)};
+    Fr s3[3] = {Fr::zero(), ldg_fr(e + 1), ldg_fr(e + 2)};             // c1, c2 only (c0 is derived from the running claim)
     Fr x0 = ldg_fr(V4 + (w & 0xffffu));
     if (Q == 32) {
       const Fr* e1 = L3 + ((size_t)65536 + (w >> 16)) * 3;
-      s3[0] = add(s3[0], ldg_fr(e1)); s3[1] = add(s3[1], ldg_fr(e1 + 1)); s3[2] = add(s3[2], ldg_fr(e1 + 2));
+      s3[1] = add(s3[1], ldg_fr(e1 + 1)); s3[2] = add(s3[2], ldg_fr(e1 + 2));
       Fr x1 = ldg_fr(V4 + (w >> 16)), c[3];
-      out[i] = bin_pair(x0, x1, eh, v4, c);                // round 4: the element's two halves
+      out[i] = bin_pair_c12(x0, x1, eh, v4, c);            // round 4: the element's two halves
 #pragma unroll
-      for (int k = 0; k < 3; ++k) acc[3 + k] = add(acc[3 + k], c[k]);
+      for (int k = 1; k < 3; ++k) acc[3 + k] = add(acc[3 + k], c[k]);
     } else {
       out[i] = x0;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) acc[k] = add(acc[k], mul(eh, s3[k]));
+    for (int k = 1; k < 3; ++k) acc[k] = add(acc[k], mul(eh, s3[k]));
   }
   __shared__ Fr red[3 * 32];
   block_reduce_fr<3>(acc, red);
@@ -194,10 +196,15 @@ __global__ void __launch_bounds__(256, 2) k_bin_r34(const T* __restrict__ packed
 #pragma unroll
     for (int k = 0; k < NACC; ++k) partials[blockIdx.x * NACC + k] = acc[k];
 }
-// proof[0 .. 3 * ROUNDS) from the per-CTA partials: (0, -S0, S0), S1, S2 from k_bin_packed3, then S3 (, S4) from k_bin_r34
+// proof[0 .. 3 * rounds) from the per-CTA partials.  The cells are exactly 0 / 1, so the sumcheck's claim starts at 0 and
+// round 0 is (0, -S0, S0); for every later packed round only c1 and c2 were summed and c0 = claim_j - u_j (c1 + c2) with
+// claim_{j+1} = c0 + v_j (c1 + v_j c2)  (the verifier's own identities, exact in the field).  claim_out = the claim the generic
+// rounds continue from.
 __global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict__ partials, unsigned nparts, const Fr* __restrict__ partials2, unsigned nparts2,
-                                                           int nacc2, Fr* __restrict__ proof) {
+                                                           int nacc2, const Fr* __restrict__ u, const Fr* __restrict__ v, Fr* __restrict__ proof,
+                                                           Fr* __restrict__ claim_out) {
   __shared__ Fr red[3 * 32];
+  __shared__ Fr sums[13];
   Fr acc[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) acc[k] = Fr::zero();
@@ -209,10 +216,9 @@ __global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict_
   block_reduce_fr<3>(acc + 3, red);
   __syncthreads();
   block_reduce_fr<1>(acc + 6, red);
-  if (threadIdx.x == 0) {
-    proof[0] = Fr::zero(); proof[1] = neg(acc[0]); proof[2] = acc[0];
-    for (int k = 0; k < 6; ++k) proof[3 + k] = acc[1 + k];
-  }
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) sums[k] = acc[k];
   __syncthreads();
   Fr b[6];
 #pragma unroll
@@ -222,8 +228,21 @@ __global__ void __launch_bounds__(256) k_bin_packed_finish(const Fr* __restrict_
   block_reduce_fr<3>(b, red);
   __syncthreads();
   block_reduce_fr<3>(b + 3, red);
-  if (threadIdx.x == 0)
-    for (int k = 0; k < nacc2; ++k) proof[9 + k] = b[k];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) sums[7 + k] = b[k];
+    // sums: [0] S0 | [1..3] round 1 | [4..6] round 2 | [7..9] round 3 | [10..12] round 4   (c0 slots unused)
+    const int rounds = 3 + nacc2 / 3;
+    proof[0] = Fr::zero(); proof[1] = neg(sums[0]); proof[2] = sums[0];
+    Fr claim = add(proof[0], mul(v[0], add(proof[1], mul(v[0], proof[2]))));
+    for (int r = 1; r < rounds; ++r) {
+      const Fr c1 = sums[3 * r - 1], c2 = sums[3 * r];
+      const Fr c0 = sub(claim, mul(u[r], add(c1, c2)));
+      proof[3 * r] = c0; proof[3 * r + 1] = c1; proof[3 * r + 2] = c2;
+      claim = add(c0, mul(v[r], add(c1, mul(v[r], c2))));
+    }
+    *claim_out = claim;
+  }
 }
 
 // partial_me(u, Q) of a 0/1 table: out[bit] = sum over elements with that bit set of eq(u, elem).  Lane = bit.
@@ -297,21 +316,24 @@ static int packed_bin_and_recover(const T* packed, size_t n, size_t L, const zkd
   if ((rc = parts.alloc(sizeof(Fr) * 7 * grid, st))) return rc;
   size_t smem = sizeof(Fr) * PL::OFF_V3;
   ZK_CUDA(cudaFuncSetAttribute(k_bin_packed3<Q, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // rounds 0..2 over Q n cells of 32 B by SURVEY.md §8d's Fr-cell model: 96 Q n (1 - 1/8) B; real traffic (sizeof(T) + 32) n B; 7 products per element
-  ZK_LAUNCH_P(st, 96.0 * Q * n * 0.875, 7.0 * n, 0.0, k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), parts.as<Fr>()));
+  // rounds 0..2 over Q n cells of 32 B by SURVEY.md §8d's Fr-cell model: 96 Q n (1 - 1/8) B; real traffic (sizeof(T) + 32) n B; 5 products per element
+  ZK_LAUNCH_P(st, 96.0 * Q * n * 0.875, 5.0 * n, 0.0, k_bin_packed3<Q, T><<<grid, 512, smem, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), parts.as<Fr>()));
   constexpr int NACC = 3 * (PL::ROUNDS - 3);
   unsigned grid2 = (unsigned)num_sms() * 4;
   if ((size_t)grid2 * 256 > n) grid2 = div_up(n, 256);
   Scratch parts2;
   if ((rc = parts2.alloc(sizeof(Fr) * NACC * grid2, st))) return rc;
   Fr v4; for (int i = 0; i < 8; ++i) v4.v[i] = v_host[4].val[i];
-  // rounds 3 (and 4): tables of Q n / 8 (and Q n / 16) cells in the Fr-cell model; 3 (+ 6) products per element
-  ZK_LAUNCH_P(st, 48.0 * (Q * n / 8) * (Q == 32 ? 1.5 : 1.0), (Q == 32 ? 9.0 : 3.0) * n, 0.0,
+  // rounds 3 (and 4): tables of Q n / 8 (and Q n / 16) cells in the Fr-cell model; 2 (+ 4) products per element
+  ZK_LAUNCH_P(st, 48.0 * (Q * n / 8) * (Q == 32 ? 1.5 : 1.0), (Q == 32 ? 6.0 : 2.0) * n, 0.0,
               k_bin_r34<Q, T><<<grid2, 256, 0, st>>>(packed, n, ehi.as<Fr>(), lut.as<Fr>(), v4, a3.as<Fr>(), parts2.as<Fr>()));
-  ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, parts2.as<Fr>(), grid2, NACC, proof_sc));
-  // remaining rounds on the folded table: binary_sumcheck(a, u[R:], v[R:]) has exactly those rounds and the final a(0)
+  Scratch claim;
+  if ((rc = claim.alloc(sizeof(Fr), st))) return rc;
+  ZK_LAUNCH(k_bin_packed_finish<<<1, 256, 0, st>>>(parts.as<Fr>(), grid, parts2.as<Fr>(), grid2, NACC, ud.as<Fr>(), vd.as<Fr>(), proof_sc, claim.as<Fr>()));
+  // remaining rounds on the folded table: binary_sumcheck(a, u[R:], v[R:]) has exactly those rounds and the final a(0); they
+  // continue from the running claim, so they too sum only c1 and c2
   constexpr int R = PL::ROUNDS;
-  if ((rc = zkdl_bin_sumcheck(a3.as<zkdl_fr_t>(), n, u_host + R, v_host + R, k - R, reinterpret_cast<zkdl_fr_t*>(proof_sc + 3 * R), st))) return rc;
+  if ((rc = bin_sumcheck_continue(a3.as<Fr>(), n, u_host + R, v_host + R, k - R, claim.as<Fr>(), proof_sc + 3 * R, st))) return rc;
   // partial_me(u_recover, Q)
   unsigned rgrid = (unsigned)num_sms() * 2;
   if ((size_t)rgrid * 8 * 4 > n) rgrid = div_up(n, 32);
