@@ -35,11 +35,6 @@ void hs_ip_pair(const Fr* a0, const Fr* a1, const Fr* b0, const Fr* b1, const Fr
 void hs_bin_pair(const Fr* a0, const Fr* a1, const Fr* e, const Fr* x, Fr* c, Fr* ao, size_t n) {
   for (size_t i = 0; i < n; ++i) ao[i] = bin_pair(a0[i], a1[i], e[i], *x, c + 3 * i);
 }
-int hs_ip_pair_bits(const Fr* a0, const Fr* a1, const Fr* b0, const Fr* b1, const Fr* e, const Fr* x, Fr* c, Fr* ao, Fr* bo, size_t n) {
-  int taken = 0;
-  for (size_t i = 0; i < n; ++i) taken += ip_pair_weighted_bits(a0[i], a1[i], b0[i], b1[i], e[i], *x, c + 3 * i, ao[i], bo[i]) ? 1 : 0;
-  return taken;
-}
 void hs_bin_pair_c12(const Fr* a0, const Fr* a1, const Fr* e, const Fr* x, Fr* c, Fr* ao, size_t n) {
   for (size_t i = 0; i < n; ++i) ao[i] = bin_pair_c12(a0[i], a1[i], e[i], *x, c + 3 * i);
 }

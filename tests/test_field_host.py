@@ -83,16 +83,6 @@ def test_sumcheck_pair_math(hs):
         wgt = (lambda v: orc.fr_mul(e, v)) if weighted else (lambda v: v)
         assert np.array_equal(c[0::3], wgt(c0)) and np.array_equal(c[1::3], wgt(c1)) and np.array_equal(c[2::3], wgt(c2))
         assert np.array_equal(ao, orc.fr_add(a0, orc.fr_mul(xs, da))) and np.array_equal(bo, orc.fr_add(b0, orc.fr_mul(xs, db)))
-    # 0/1 second operand (round 0 of zkReLU's Hadamard sumcheck): the selection form gives the same elements; general operands decline
-    one = orc.fr_mont(orc.to_limbs([1]))[0]
-    bits0 = np.where((np.arange(n) % 2 == 0)[:, None], one[None, :], 0).astype(np.uint32)
-    bits1 = np.where((np.arange(n) % 4 < 2)[:, None], one[None, :], 0).astype(np.uint32)
-    cw = np.zeros((3 * n, 8), np.uint32); aw = np.zeros_like(a0); bw = np.zeros_like(a0)
-    hs.hs_ip_pair(p(a0), p(a1), p(bits0), p(bits1), p(e), p(x), 1, p(cw), p(aw), p(bw), C.c_size_t(n))
-    cb = np.zeros((3 * n, 8), np.uint32); ab = np.zeros_like(a0); bb = np.zeros_like(a0)
-    assert hs.hs_ip_pair_bits(p(a0), p(a1), p(bits0), p(bits1), p(e), p(x), p(cb), p(ab), p(bb), C.c_size_t(n)) == n
-    assert np.array_equal(cb, cw) and np.array_equal(ab, aw) and np.array_equal(bb, bw)
-    assert hs.hs_ip_pair_bits(p(a0), p(a1), p(b0), p(b1), p(e), p(x), p(cb), p(ab), p(bb), C.c_size_t(n - 5)) == 0
     c = np.zeros((3 * n, 8), np.uint32); ao = np.zeros_like(a0)
     hs.hs_bin_pair(p(a0), p(a1), p(e), p(x), p(c), p(ao), C.c_size_t(n))
     assert np.array_equal(c[0::3], orc.fr_mul(e, orc.fr_sub(orc.fr_mul(a0, a0), a0)))

@@ -26,24 +26,6 @@ ZK_HD void ip_pair(const Fr& a0, const Fr& a1, const Fr& b0, const Fr& b1, const
   b_out = add(b0, mul(x, db));
 }
 
-// The same weighted pair when b0 and b1 are each exactly 0 or 1 (Montgomery one): round 0 of zkReLU's Hadamard sumcheck, whose
-// second table is the 0/1 `sign` table (zkrelu.cu:99).  Every product with b degenerates into a selection: 3 products
-// instead of 7, same field elements.  Returns false (nothing written) when the operands are not of that form.
-ZK_HD bool ip_pair_weighted_bits(const Fr& a0, const Fr& a1, const Fr& b0, const Fr& b1, const Fr& e, const Fr& x, Fr* c, Fr& a_out, Fr& b_out) {
-  const Fr one = Fr::one();
-  const bool z0 = b0.is_zero(), o0 = !z0 && b0 == one, z1 = b1.is_zero(), o1 = !z1 && b1 == one;
-  if (!((z0 || o0) && (z1 || o1))) return false;
-  Fr da = sub(a1, a0);
-  Fr wa0 = mul(e, a0), wda = mul(e, da);
-  c[0] = o0 ? wa0 : Fr::zero();
-  c[2] = o1 == o0 ? Fr::zero() : (o1 ? wda : neg(wda));                 // wda * (b1 - b0)
-  Fr t = o1 ? add(wa0, wda) : Fr::zero();                                // (wa0 + wda) * b1
-  c[1] = sub(sub(t, c[0]), c[2]);
-  a_out = add(a0, mul(x, da));
-  b_out = o1 == o0 ? b0 : (o1 ? x : sub(one, x));                        // b0 + x (b1 - b0)
-  return true;
-}
-
 // Fr_bin_sc_step coefficients (/root/reference/proof.cu:152-163) weighted by e, plus the fold with x:
 //   c0 = a0^2 - a0 = a0 (a0 - 1), c1 = 2 a0 d - d = d (2 a0 - 1), c2 = d^2, d = a1 - a0
 ZK_HD Fr bin_pair(const Fr& a0, const Fr& a1, const Fr& e, const Fr& x, Fr* c) {

@@ -170,7 +170,7 @@ __device__ __forceinline__ void sc_round_items(const Fr* __restrict__ a, const F
         Fr b1 = g1 < in_size ? b[g1] : Fr::zero();
         if (KIND == SC_HP) {
           const Fr& e = t ? e1 : e0;
-          if (!ip_pair_weighted_bits(a0, a1, b0, b1, e, x, c, a_out[g], b_out[g])) ip_pair<true>(a0, a1, b0, b1, e, x, c, a_out[g], b_out[g]);
+          ip_pair<true>(a0, a1, b0, b1, e, x, c, a_out[g], b_out[g]);
         } else {
           ip_pair<false>(a0, a1, b0, b1, a0, x, c, a_out[g], b_out[g]);
         }
