@@ -191,7 +191,7 @@ __device__ __forceinline__ Fr ldcg_fr(const Fr* p) {          // L2 load (other 
 // DERIVE (binary sumcheck, every round after the first): only c1 and c2 are summed; c0 follows from the running claim kept in
 // `claim` (device), which every round's last CTA advances: claim_{j+1} = c0 + x (c1 + x c2), x = this round's fold challenge.
 template <int KIND, bool DERIVE>
-__global__ void __launch_bounds__(THREADS) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
+__global__ void __launch_bounds__(THREADS, 2) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
                                                       const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x, size_t in_size, size_t out_size,
                                                       size_t H, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof3,
                                                       Fr uj, Fr* __restrict__ claim) {
