@@ -480,6 +480,128 @@ __global__ void __launch_bounds__(128) k_msm_reduce_scan(const G1XYZZ* __restric
   }
   if (t == 0) { if (FINAL) out[blockIdx.x] = xyzz_to_jac(val); else group_out[blockIdx.x] = val; }
 }
+// ---- cooperative bucket reduction for the few-rows case (one opening alone on a GPU).  A dependent XYZZ addition costs a lone
+// warp ~15 us (14 Fq products whose carry chains serialise; tools/addlat.cu), and k_msm_reduce_scan is 16 of them in a row.
+// Here the FOUR warps of a CTA share every addition of 32 point slots: the products of one dependency level run on four
+// different warp schedulers at once (u1 | u2 | s1 | s2, then zz1 zz2 | zzz1 zzz2 | p^2 | r^2, then p^3 | u1 p^2 | zz p^2,
+// then s1 p^3 | r (q - x3) | zzz p^3): 4 product latencies per addition instead of 14.  Operands live in shared memory as
+// structure-of-arrays (field, limb, slot): conflict-free, and a slot may read another slot's point (the scan).  All reads of a
+// call precede all its writes, so `out` may alias an operand.  Infinity operands copy the other one; equal abscissae (P + P,
+// P - P: structured inputs only) fall back to the complete single-thread formula for that slot.
+struct CoopArr { uint32_t w[4][12][32]; };                       // 32 XYZZ points: x, y, zz, zzz
+struct CoopTmp { uint32_t t[11][12][32]; uint32_t slow[32]; };
+enum { CT_U1, CT_U2, CT_S1, CT_S2, CT_ZZ12, CT_ZZZ12, CT_P, CT_PP, CT_R, CT_PPP_Q_BASE };   // RR, PPP, Q, Y3B share the tail slots
+__device__ __forceinline__ Fq cld(const uint32_t (*f)[32], int slot) { Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) r.v[i] = f[i][slot];
+  return r; }
+__device__ __forceinline__ void cst(uint32_t (*f)[32], int slot, const Fq& v) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) f[i][slot] = v.v[i]; }
+__device__ __forceinline__ G1XYZZ cld_pt(const CoopArr& A, int slot) { G1XYZZ p; p.x = cld(A.w[0], slot); p.y = cld(A.w[1], slot); p.zz = cld(A.w[2], slot); p.zzz = cld(A.w[3], slot); return p; }
+__device__ __forceinline__ void cst_pt(CoopArr& A, int slot, const G1XYZZ& p) { cst(A.w[0], slot, p.x); cst(A.w[1], slot, p.y); cst(A.w[2], slot, p.zz); cst(A.w[3], slot, p.zzz); }
+
+// out[lane] = A[ia] + B[ib] for the lanes with `active`; every thread of the 128-thread CTA must call it
+__device__ __noinline__ void coop_add(CoopArr& out, const CoopArr& A, int ia, const CoopArr& B, int ib, bool active, CoopTmp& T, int warp, int lane) {
+  uint32_t (*U1)[32] = T.t[0], (*U2)[32] = T.t[1], (*S1)[32] = T.t[2], (*S2)[32] = T.t[3], (*ZZ12)[32] = T.t[4], (*ZZZ12)[32] = T.t[5];
+  uint32_t (*P)[32] = T.t[6], (*PP)[32] = T.t[7], (*R)[32] = T.t[8], (*PPP)[32] = T.t[9], (*Q)[32] = T.t[10];
+  uint32_t (*RR)[32] = T.t[1], (*Y3B)[32] = T.t[3];                 // U2 / S2 are dead once p and r exist
+  bool a_inf = false, b_inf = false;
+  if (active) {
+    uint32_t za = 0, zb = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { za |= A.w[2][i][ia]; zb |= B.w[2][i][ib]; }
+    a_inf = za == 0; b_inf = zb == 0;
+  }
+  const bool live = active && !a_inf && !b_inf;
+  if (live) {
+    if (warp == 0) cst(U1, lane, mul(cld(A.w[0], ia), cld(B.w[2], ib)));
+    else if (warp == 1) cst(U2, lane, mul(cld(B.w[0], ib), cld(A.w[2], ia)));
+    else if (warp == 2) cst(S1, lane, mul(cld(A.w[1], ia), cld(B.w[3], ib)));
+    else cst(S2, lane, mul(cld(B.w[1], ib), cld(A.w[3], ia)));
+  }
+  __syncthreads();
+  Fq rr_keep = Fq::zero();
+  if (live) {
+    if (warp == 0) cst(ZZ12, lane, mul(cld(A.w[2], ia), cld(B.w[2], ib)));
+    else if (warp == 1) cst(ZZZ12, lane, mul(cld(A.w[3], ia), cld(B.w[3], ib)));
+    else if (warp == 2) { Fq p = sub(cld(U2, lane), cld(U1, lane)); cst(P, lane, p); cst(PP, lane, sqr(p)); T.slow[lane] = p.is_zero() ? 1u : 0u; }
+    else { Fq r = sub(cld(S2, lane), cld(S1, lane)); cst(R, lane, r); rr_keep = sqr(r); }
+  } else if (warp == 2) T.slow[lane] = 0u;
+  __syncthreads();
+  if (live && warp == 3) cst(RR, lane, rr_keep);                     // U2 is dead now (p was formed before the barrier)
+  const bool slow = live && T.slow[lane] != 0u;
+  Fq keep = Fq::zero();
+  if (live && !slow) {
+    if (warp == 0) cst(PPP, lane, mul(cld(P, lane), cld(PP, lane)));
+    else if (warp == 1) cst(Q, lane, mul(cld(U1, lane), cld(PP, lane)));
+    else if (warp == 2) keep = mul(cld(ZZ12, lane), cld(PP, lane));   // zz3
+  }
+  __syncthreads();
+  G1XYZZ res;                                                          // slow path only (warp 0)
+  if (live && !slow) {
+    if (warp == 0 || warp == 1) {
+      Fq q = cld(Q, lane), ppp = cld(PPP, lane);
+      Fq x3 = sub(sub(sub(cld(RR, lane), ppp), q), q);
+      if (warp == 0) { keep = x3; cst(Y3B, lane, mul(cld(S1, lane), ppp)); }      // S2 is dead (r was formed two barriers ago)
+      else keep = mul(cld(R, lane), sub(q, x3));                                  // y3a
+    } else if (warp == 3) keep = mul(cld(ZZZ12, lane), cld(PPP, lane));           // zzz3
+  } else if (active && a_inf) keep = cld(B.w[warp], ib);                          // inf + b = b (all reads before any write)
+  else if (active && b_inf) keep = cld(A.w[warp], ia);
+  else if (slow && warp == 0) res = xyzz_add(cld_pt(A, ia), cld_pt(B, ib));       // P + P or P - P: the complete formula
+  __syncthreads();
+  if (active) {
+    if (slow) { if (warp == 0) cst_pt(out, lane, res); }
+    else {
+      if (live && warp == 1) keep = sub(keep, cld(Y3B, lane));
+      cst(out.w[warp], lane, keep);
+    }
+  }
+  __syncthreads();
+}
+
+// One CTA of 128 threads per row of K = 128 buckets: slot t owns buckets 4t..4t+3.
+//   A  running sums: run_t = sum of the slot's buckets, tot_t = their sum with weights 1..4        (6 additions)
+//   B  E_t = inclusive suffix sum of run over the slots, in place                                    (5)
+//   C  sum_b (b+1) B_b = sum_t tot_t + 4 sum_{t>=1} E_t: both sums by one tree (first step apart, then packed 16 + 16)   (6)
+//   D  thread 0: T + [4] F, to Jacobian
+template <bool FINAL>
+__global__ void __launch_bounds__(128) k_msm_reduce_coop(const G1XYZZ* __restrict__ buckets, G1XYZZ* __restrict__ group_out, G1Jac* __restrict__ out) {
+  __shared__ CoopArr RUN, TOT, OPB;
+  __shared__ CoopTmp T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const G1XYZZ* B = buckets + (size_t)blockIdx.x * 128;
+  auto load_field = [&](const G1XYZZ& p) -> Fq { return warp == 0 ? p.x : (warp == 1 ? p.y : (warp == 2 ? p.zz : p.zzz)); };
+  {
+    Fq v = load_field(B[4 * lane + 3]);
+    cst(RUN.w[warp], lane, v); cst(TOT.w[warp], lane, v);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int b = 2; b >= 0; --b) {
+    cst(OPB.w[warp], lane, load_field(B[4 * lane + b]));
+    __syncthreads();
+    coop_add(RUN, RUN, lane, OPB, lane, true, T, warp, lane);
+    coop_add(TOT, TOT, lane, RUN, lane, true, T, warp, lane);
+  }
+#pragma unroll 1
+  for (int d = 1; d < 32; d <<= 1) coop_add(RUN, RUN, lane, RUN, (lane + d) & 31, lane + d < 32, T, warp, lane);   // RUN -> E
+  // tree, first step per sum; slot 0 of E is excluded from F
+  if (lane == 0) { Fq z = Fq::zero(); if (warp >= 2) cst(RUN.w[warp], 0, z); }                                   // E_0 := infinity
+  __syncthreads();
+  coop_add(TOT, TOT, lane, TOT, (lane + 16) & 31, lane < 16, T, warp, lane);
+  coop_add(RUN, RUN, lane, RUN, (lane + 16) & 31, lane < 16, T, warp, lane);
+  if (lane >= 16) cst(TOT.w[warp], lane, cld(RUN.w[warp], lane - 16));                                           // pack: TOT[16..31] = partial F
+  __syncthreads();
+#pragma unroll 1
+  for (int off = 8; off > 0; off >>= 1) coop_add(TOT, TOT, lane, TOT, (lane + off) & 31, (lane & 15) < off, T, warp, lane);
+  if (threadIdx.x == 0) {
+    G1XYZZ Tt = cld_pt(TOT, 0), F = cld_pt(TOT, 16);
+    G1XYZZ r = xyzz_add(Tt, xyzz_dbl(xyzz_dbl(F)));
+    if (FINAL) out[blockIdx.x] = xyzz_to_jac(r); else group_out[blockIdx.x] = r;
+  }
+}
+
 __global__ void __launch_bounds__(64) k_msm_final(const G1XYZZ* __restrict__ groups, size_t m, int NG, int split, int c, G1Jac* __restrict__ out) {
   size_t row = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (row >= m) return;
@@ -657,6 +779,11 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
     // few buckets per group: register/shuffle reduction, one CTA per group; 32 threads when rows are plentiful, 128 otherwise
     int T = ngroups >= (size_t)num_sms() * 2 ? 32 : 128;
     if (T > cfg.K) T = cfg.K < 32 ? 32 : cfg.K;
+    static const bool no_coop = getenv("ZKDL_MSM_NO_COOP") != nullptr;      // A/B knob
+    if (cfg.K == 128 && T == 128 && cfg.NG == 1 && !no_coop) {               // few rows: latency matters, four warps share every addition
+      ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce_coop<true><<<(unsigned)ngroups, 128, 0, st>>>(buckets.as<G1XYZZ>(), nullptr, out));
+      return ZK_OK;
+    }
     if (cfg.NG == 1) {
       ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce_scan<true><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, nullptr, out));
       return ZK_OK;
