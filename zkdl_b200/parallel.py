@@ -28,14 +28,14 @@ def _clog2(n):
 
 def subtask_cost(kind, mask, I, O, B):
     """Latency (ms) of one piece run alone on an idle B200, fitted to tools/probe_subtasks.py on the demo shapes
-    (round 2 build: gpurun_out/r2c/subtasks.log -> profiles/r2_subtask_latencies_b200.json)."""
+    (round-2 build: profiles/r2_subtask_latencies_b200.json)."""
     if kind == "fc":
         if mask == 1:
-            return 0.16 + 0.023 * (I * O / 2 ** 20)                          # X / W folds + inner-product sumcheck + Z(u)
+            return 0.134 + 0.019 * (I * O / 2 ** 20)                         # X / W folds + inner-product sumcheck + Z(u)
         ngens = 1 << ((_clog2(I * O) + 1) // 2)                              # demo.cu:81 on the padded shape
-        return 0.56 + 0.35 * (ngens / 1024)                                  # opening: one batched MSM over |G| generators
+        return 0.37 + 0.335 * (ngens / 1024)                                 # opening: one batched MSM over |G| generators
     n = B * O / 2 ** 20
-    return {1: 0.37 + 0.83 * n, 2: 0.34 + 0.61 * n, 4: 0.24 + 0.27 * n}[mask]
+    return {1: 0.35 + 0.68 * n, 2: 0.31 + 0.56 * n, 4: 0.222 + 0.232 * n}[mask]
 
 
 def partition_subtasks(shapes, B, world, costs=None):
