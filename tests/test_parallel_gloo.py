@@ -184,7 +184,7 @@ def test_subtask_partition_covers_every_piece_once_and_balances():
                 seen[key] = seen.get(key, 0) | mask
         assert all(seen[("fc", i)] == 3 for i in range(8)) and all(seen[("relu", i)] == 7 for i in range(7))
         assert ("relu", 7) not in seen
-        loads = [sum(parallel.subtask_cost(k[0], m, *DEMO_SHAPES[k[1]], 256) for k, mk in p.items() for m in (1, 2, 4) if mk & m)
+        loads = [sum(parallel.subtask_cost(k[0], m, *DEMO_SHAPES[k[1]], 256, world) for k, mk in p.items() for m in (1, 2, 4) if mk & m)
                  for p in plan]
         assert max(loads) <= 1.15 * (sum(loads) / world) + 1e-9
 

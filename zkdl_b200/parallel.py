@@ -26,16 +26,22 @@ def _clog2(n):
     return 0 if n <= 1 else (int(n) - 1).bit_length()
 
 
-def subtask_cost(kind, mask, I, O, B):
-    """Latency (ms) of one piece run alone on an idle B200, fitted to tools/probe_subtasks.py on the demo shapes
-    (round-2 build: profiles/r2_subtask_latencies_b200.json)."""
-    if kind == "fc":
-        if mask == 1:
-            return 0.134 + 0.019 * (I * O / 2 ** 20)                         # X / W folds + inner-product sumcheck + Z(u)
-        ngens = 1 << ((_clog2(I * O) + 1) // 2)                              # demo.cu:81 on the padded shape
-        return 0.37 + 0.335 * (ngens / 1024)                                 # opening: one batched MSM over |G| generators
+def subtask_cost(kind, mask, I, O, B, world=8):
+    """Cost (ms) of one piece for the longest-first plan.  With many ranks a rank holds a handful of pieces and is bound by
+    their LATENCY (the piece alone on an idle B200, tools/probe_subtasks.py); with two ranks each GPU is as busy as a
+    single one and is bound by the pieces' THROUGHPUT share (an opening is mostly bucket accumulation on every SM, a
+    sumcheck mostly short launches).  The cost blends the two by world size.  Fitted on the demo shapes with the round-2
+    build (profiles/r2_subtask_latencies_b200.json)."""
     n = B * O / 2 ** 20
-    return {1: 0.35 + 0.68 * n, 2: 0.31 + 0.56 * n, 4: 0.222 + 0.232 * n}[mask]
+    if kind == "fc":
+        ngens = 1 << ((_clog2(I * O) + 1) // 2)                              # demo.cu:81 on the padded shape
+        lat = 0.134 + 0.019 * (I * O / 2 ** 20) if mask == 1 else 0.37 + 0.335 * (ngens / 1024)
+        thr = 0.03 + 0.01 * (I * O / 2 ** 20) if mask == 1 else 0.08 + 0.33 * (ngens / 1024)
+    else:
+        lat = {1: 0.35 + 0.68 * n, 2: 0.31 + 0.56 * n, 4: 0.222 + 0.232 * n}[mask]
+        thr = {1: 0.46 * n, 2: 0.33 * n, 4: 0.25 * n}[mask]
+    w = min(1.0, max(0.0, (world - 1) / 7.0))
+    return w * lat + (1.0 - w) * thr
 
 
 def partition_subtasks(shapes, B, world, costs=None):
@@ -49,7 +55,7 @@ def partition_subtasks(shapes, B, world, costs=None):
         if i + 1 < len(shapes):
             for m in RELU_MASKS:
                 pieces.append((("relu", i), m, I, O))
-    cost = lambda pc: (costs or {}).get((pc[0], pc[1]), subtask_cost(pc[0][0], pc[1], pc[2], pc[3], B))
+    cost = lambda pc: (costs or {}).get((pc[0], pc[1]), subtask_cost(pc[0][0], pc[1], pc[2], pc[3], B, world))
     pieces.sort(key=lambda pc: (-cost(pc), pc[0][1], pc[0][0], pc[1]))
     load = [0.0] * world
     plan = [dict() for _ in range(world)]
