@@ -45,5 +45,5 @@ for path in sys.argv[2:]:
 json.dump(out, open(sys.argv[1], "w"), indent=1)
 for e in out:
     print(f"{e['kernel'][:44]:44s} {e.get('time_us', 0):8.1f}us grid {int(e.get('grid', 0)):6d} x {int(e.get('block', 0)):4d} regs {int(e.get('regs', 0)):3d} "
-          f"sm {e.get('sm_throughput_pct', 0):5.1f}% fma {e.get('fma_pipe_pct', 0):5.1f}% alu {e.get('alu_pipe_pct', 0):5.1f}% tensor {e.get('tensor_pipe_pct', 0):5.1f}% "
+          f"sm {e.get('sm_throughput_pct', 0):5.1f}% imad(fmaheavy) {e.get('fmaheavy_pipe_pct', 0):5.1f}% alu {e.get('alu_pipe_pct', 0):5.1f}% tensor {e.get('tensor_pipe_pct', 0):5.1f}% "
           f"warps {e.get('warps_active_pct', 0):5.1f}% dram {e.get('dram_pct', 0):5.1f}% ({e.get('dram_bytes', 0) / 1e6:8.1f} MB) L2hit {e.get('l2_hit_pct', 0):5.1f}%")
