@@ -11,7 +11,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libzkdl_b200.so")
+LIB_PATH = os.environ.get("ZKDL_LIB", os.path.join(_HERE, "libzkdl_b200.so"))      # ZKDL_LIB: A/B a differently tuned build of the same library
 HEADER_PATH = os.path.join(_ROOT, "include", "zkdl_b200.h")
 _lib = None
 

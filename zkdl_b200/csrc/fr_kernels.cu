@@ -21,6 +21,9 @@ namespace zk {
 static constexpr int THREADS = 256;
 static constexpr size_t TAIL_N = 2048;        // tables this small finish in one single-CTA launch
 static constexpr int TAIL_THREADS = 512;
+#ifndef FOLD3_MIN_CTAS
+#define FOLD3_MIN_CTAS 6                      // CTAs of 128 threads per SM the three-round fold is compiled for (register cap)
+#endif
 
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline const Fr* F(const zkdl_fr_t* p) { return reinterpret_cast<const Fr*>(p); }
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_fr_sum_final(const Fr* __restr
 // R fold rounds in one pass over rows of `window` columns: out[r', c] = fold_R(in[r' * 2^R + 0..2^R-1, c]);
 // window == 1 is Fr_me_step applied R times, window > 1 is Fr_partial_me_step applied R times.  Missing rows are 0.
 template <int R>
-__global__ void __launch_bounds__(THREADS) k_fr_fold_multi(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict__ xs,
+__global__ void __launch_bounds__(R == 3 ? 128 : THREADS, R == 3 ? FOLD3_MIN_CTAS : 1) k_fr_fold_multi(const Fr* __restrict__ in, Fr* __restrict__ out, const Fr* __restrict__ xs,
                                                            size_t in_size, size_t out_rows, size_t window) {
   Fr x[R];
 #pragma unroll
@@ -435,7 +438,7 @@ static int fold_driver(const Fr* a, size_t n, const zkdl_fr_t* u_host, size_t k,
     Fr* dst = bufs[which];
     size_t total = out_rows * w;
     static const int fold_block = getenv("ZKDL_FOLD_BLOCK") ? atoi(getenv("ZKDL_FOLD_BLOCK")) : 128;     // tuning knob
-    static const int fold_cap = getenv("ZKDL_FOLD_CAP") ? atoi(getenv("ZKDL_FOLD_CAP")) : 16;
+    static const int fold_cap = getenv("ZKDL_FOLD_CAP") ? atoi(getenv("ZKDL_FOLD_CAP")) : 48;
     size_t blocks = (total + fold_block - 1) / fold_block, capb = (size_t)num_sms() * fold_cap;
     unsigned grid = (unsigned)(blocks < capb ? (blocks ? blocks : 1) : capb);
     // 48 n B per round, R rounds fused = 96 n (1 - 2^-R) B algorithmic (real traffic: 32 n (1 + 2^-R)); 2^R - 1 products per output
