@@ -21,6 +21,9 @@ namespace zk {
 static constexpr int THREADS = 256;
 static constexpr size_t TAIL_N = 2048;        // tables this small finish in one single-CTA launch
 static constexpr int TAIL_THREADS = 512;
+#ifndef SC_MIN_CTAS
+#define SC_MIN_CTAS 2                         // CTAs of 256 threads per SM the sumcheck round kernels are compiled for
+#endif
 #ifndef FOLD3_MIN_CTAS
 #define FOLD3_MIN_CTAS 6                      // CTAs of 128 threads per SM the three-round fold is compiled for (register cap)
 #endif
@@ -194,7 +197,7 @@ __device__ __forceinline__ Fr ldcg_fr(const Fr* p) {          // L2 load (other 
 // DERIVE (binary sumcheck, every round after the first): only c1 and c2 are summed; c0 follows from the running claim kept in
 // `claim` (device), which every round's last CTA advances: claim_{j+1} = c0 + x (c1 + x c2), x = this round's fold challenge.
 template <int KIND, bool DERIVE>
-__global__ void __launch_bounds__(THREADS, 2) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
+__global__ void __launch_bounds__(THREADS, SC_MIN_CTAS) k_sc_round(const Fr* __restrict__ a, const Fr* __restrict__ b, Fr* __restrict__ a_out, Fr* __restrict__ b_out,
                                                       const Fr* __restrict__ e_in, Fr* __restrict__ e_out, Fr x, size_t in_size, size_t out_size,
                                                       size_t H, Fr* __restrict__ partials, unsigned* __restrict__ counter, Fr* __restrict__ proof3,
                                                       Fr uj, Fr* __restrict__ claim) {
