@@ -374,23 +374,22 @@ def main():
     # ---- N > 1: the two north_star splits on their own workloads (every rank takes part; timed as the max over ranks)
     if world > 1:
         reps = 3
-        lgN = 24
-        lo, hi = parallel.shard_range(1 << lgN, world, rank)
-        rng = np.random.default_rng(100 + rank)
-        ks = rng.integers(0, 1 << 32, size=(hi - lo, 8), dtype=np.uint64).astype(np.uint32); ks[:, 7] %= 1944954707
-        G = zk.g1_mul(zk.to_device(mlp._generator()), zk.to_device(ks))
-        tab = zk.G1Table(G, full=False); del G
-        sc = rng.integers(0, 1 << 32, size=(hi - lo, 8), dtype=np.uint64).astype(np.uint32); sc[:, 7] %= 1944954707
-        sc = zk.to_device(sc)
-        fn = lambda: parallel.msm_sharded(lambda: zk.msm(tab, sc, 1, False), zk.g1_sum, None, world)
-        fn(); barrier(); e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record(); barrier()
-        t_msm = max_over_ranks(e0.elapsed_time(e1) / reps)
-        tab.close(); del sc
-        extra["msm_by_point_range"] = {"log_n": lgN, "ms": t_msm, "Mpts_per_s": (1 << lgN) / t_msm / 1e3,
-                                       "what": "one 2^24-point 255-bit MSM, N/P contiguous (base, scalar) pairs per rank, all-gather of P partial points + local G1 sum"}
+        gen_pt = zk.to_device(mlp._generator())
+        for lgN, key in ((24, "msm_by_point_range"), (26, "msm_by_point_range_2^26")):      # config 3 asks for 2^16 .. 2^26 at 1/2/4/8 GPUs
+            lo, hi = parallel.shard_range(1 << lgN, world, rank)
+            G = zk.g1_mul(gen_pt, zk.fr_random(hi - lo, 1000 * lgN + rank))                 # bases [k_i] g, k_i from the curand stream
+            tab = zk.G1Table(G, full=False); del G
+            sc = zk.fr_random(hi - lo, 2000 * lgN + rank)
+            fn = lambda: parallel.msm_sharded(lambda: zk.msm(tab, sc, 1, False), zk.g1_sum, None, world)
+            fn(); barrier(); e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); barrier()
+            t_msm = max_over_ranks(e0.elapsed_time(e1) / reps)
+            tab.close(); del sc
+            extra[key] = {"log_n": lgN, "ms": t_msm, "Mpts_per_s": (1 << lgN) / t_msm / 1e3,
+                          "what": f"one 2^{lgN}-point 255-bit MSM, N/P contiguous (base, scalar) pairs per rank, all-gather of P partial points + local G1 sum"}
+            torch.cuda.empty_cache()
         k = 26
         lo, hi = parallel.shard_range(1 << k, world, rank)
         g = torch.Generator(device="cuda").manual_seed(11 + rank)
