@@ -304,8 +304,8 @@ def main():
     meta = {(k_, i): (L.I, L.ngens, P.B * L.O) for i, L in enumerate(P.layers) for k_ in ("fc", "relu")}
     proof_sizes = []
 
-    def prove_step(seed, e2e_input=None):
-        parts = P.prove(seed=seed, parts=plan) if e2e_input is None else P.forward_and_prove(e2e_input, seed=seed, parts=plan)
+    def prove_step(seed, overlap_forward=False):
+        parts = P.prove(seed=seed, parts=plan, overlap_forward=overlap_forward)
         if world == 1:
             return torch.cat([t.reshape(-1) for p in parts for t in p[2:]])
         flat = parallel.pack_owned(parts, plan, meta)   # this rank's proof segments (parallel.assemble is the inverse)
@@ -318,9 +318,8 @@ def main():
 
     def e2e_step(seed):
         xd = x_host.cuda(non_blocking=True)             # H2D of this step's input batch from pinned memory
-        # quantised forward pass + proof: the proving threads start first, every layer records an event and each piece waits
-        # only for its own layer's tables (MLPProver.forward_and_prove)
-        flat = prove_step(seed, e2e_input=xd)
+        P.forward(xd)                                   # quantised forward pass; every layer records an event ...
+        flat = prove_step(seed, overlap_forward=True)   # ... and each piece waits only for its own layer's tables
         return flat.cpu()                               # D2H of the proof elements
 
     for w in range(max(args.warmup, 3)):

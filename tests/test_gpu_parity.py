@@ -340,29 +340,3 @@ def test_subtask_partition_reproduces_the_whole_proof(zk, world):
         assert eq(zk.to_host(got[key][0]), zk.to_host(p[2]))
         if key[0] == "fc":
             assert orc.g1_eq(zk.to_host(got[key][1]), zk.to_host(p[3])).all()
-
-
-def test_forward_and_prove_overlap_gives_the_same_proof(zk):
-    """The end-to-end path (MLPProver.forward_and_prove: proving threads started before the forward pass, every piece waiting
-    only for its own layer's event) produces the proof of forward() followed by prove(), bit for bit, also for a rank's share."""
-    import torch
-    from zkdl_b200 import mlp, parallel
-    dims = [(20, 32), (32, 64), (64, 30), (30, 16)]
-    ws, x = mlp.synthetic_mlp(dims, 8, seed=3)
-    P = mlp.MLPProver(ws, gen_seed=2)
-    P.forward(x)
-    whole = P.prove(seed=11)
-    for rep in range(3):
-        got = P.forward_and_prove(x, seed=11)
-        assert len(got) == len(whole)
-        for a, b in zip(whole, got):
-            assert a[:2] == b[:2] and eq(zk.to_host(a[2]), zk.to_host(b[2]))
-            if a[0] == "fc":
-                assert orc.g1_eq(zk.to_host(a[3]), zk.to_host(b[3])).all()
-    plan = parallel.partition_subtasks([(L.I, L.O) for L in P.layers], P.B, 3)[1]
-    ref = P.prove(seed=11, parts=plan)
-    got = P.forward_and_prove(x, seed=11, parts=plan)
-    meta = {(k, i): (L.I, L.ngens, P.B * L.O) for i, L in enumerate(P.layers) for k in ("fc", "relu")}
-    assert torch.equal(parallel.pack_owned(ref, plan, meta), parallel.pack_owned(got, plan, meta))
-    got1 = P.forward_and_prove(x, seed=11, streams=1)
-    assert all(eq(zk.to_host(a[2]), zk.to_host(b[2])) for a, b in zip(whole, got1))

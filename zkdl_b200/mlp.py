@@ -55,9 +55,8 @@ class MLPProver:
         self.n_params = sum(L.in_dim * L.out_dim for L in self.layers)
         torch.cuda.synchronize()
 
-    def forward(self, x, flags=None):
-        """x: float32 CUDA [batch, in].  Keeps Z_i, A_i and the ReLU aux tables (demo.cu:23-38).  flags: one threading.Event per
-        layer, set on the host right after the layer's CUDA event is recorded (forward_and_prove)."""
+    def forward(self, x):
+        """x: float32 CUDA [batch, in].  Keeps Z_i, A_i and the ReLU aux tables (demo.cu:23-38)."""
         B = pad2(x.shape[0])
         L0 = self.layers[0]
         X = zk.float_to_fr(x.contiguous(), B, L0.I)                                          # zkfc.cu:106-115
@@ -75,34 +74,7 @@ class MLPProver:
                 cur = a
             ev = torch.cuda.Event(); ev.record()                                            # layer i's tables are final here
             self.ready.append(ev)
-            if flags is not None:
-                flags[i].set()
         return self.Z[-1]
-
-    def forward_and_prove(self, x, seed=0, parts=None, streams=8):
-        """The end-to-end path: the proving threads are started FIRST and each piece waits (on the host for the layer's flag,
-        then on its stream for the layer's CUDA event) only for its own layer's tables, while this thread enqueues the
-        forward pass: proving the first layers overlaps both the GPU time and the launch time of the rest of the pass."""
-        import threading
-        import torch
-        from concurrent.futures import ThreadPoolExecutor
-        flags = [threading.Event() for _ in self.layers]
-        if not hasattr(self, "_driver"):
-            self._driver = ThreadPoolExecutor(max_workers=1)
-        dev, main = torch.cuda.current_device(), torch.cuda.current_stream()
-        self.B = pad2(x.shape[0])                                                            # prove() sizes its challenges from B
-
-        def drive():
-            torch.cuda.set_device(dev)
-            with torch.cuda.stream(main):
-                return self.prove(seed=seed, parts=parts, streams=streams, overlap_forward=True, flags=flags)
-        fut = self._driver.submit(drive)
-        try:
-            self.forward(x, flags)
-        finally:
-            for f in flags:
-                f.set()
-        return fut.result()
 
     def check_range(self):
         """Activations outside +-2^47 are undefined in the reference (relu_kernel, zkrelu.cu:16-28); here they are
@@ -111,7 +83,7 @@ class MLPProver:
         if self.bad and int(torch.stack(self.bad).sum().item()) != 0:
             raise ValueError("zkReLU input outside +-2^47: the decomposition (and the reference's) is undefined for it")
 
-    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None, parts=None, overlap_forward=False, flags=None):
+    def prove(self, seed=0, fc_layers=None, relu_layers=None, streams=8, threads=None, parts=None, overlap_forward=False):
         """Backward proving loop (demo.cu:124-138).  Returns the proof parts in the reference's order.
         fc_layers / relu_layers restrict the work to a subset (layer-parallel multi-GPU); `parts` = {("fc"|"relu", layer):
         part mask} restricts it further to independent parts of a layer's proof (parallel.partition_subtasks): the
@@ -181,14 +153,7 @@ class MLPProver:
 
         main = torch.cuda.current_stream()
         if streams <= 1 or len(tasks) <= 1:
-            out = []
-            for t in tasks:
-                if overlap_forward:
-                    if flags is not None:
-                        flags[t[1]].wait()
-                    main.wait_event(self.ready[t[1]])
-                out.append(run(t))
-            return out
+            return [run(t) for t in tasks]
         streams = min(streams, len(tasks))
         dev = torch.cuda.current_device()
         if len(getattr(self, "_streams", [])) < streams:
@@ -227,8 +192,6 @@ class MLPProver:
             with torch.cuda.stream(st):
                 for j in order[slot::streams]:
                     if overlap_forward:
-                        if flags is not None:
-                            flags[tasks[j][1]].wait()                  # the layer's CUDA event exists only once the flag is set
                         st.wait_event(self.ready[tasks[j][1]])
                     res.append((j, run(tasks[j])))
             ev = torch.cuda.Event(); ev.record(st)
