@@ -560,6 +560,80 @@ __device__ __noinline__ void coop_add(CoopArr& out, const CoopArr& A, int ia, co
   __syncthreads();
 }
 
+// out[lane] = 2 * A[lane] for the lanes with `active` (dbl-2008-s-1, a = 0): three product levels instead of nine products in a
+// row: (2y)^2 | x^2, then u v | x v | m^2 | v zz, then m (s - x3) | w y | w zzz.  Same calling convention as coop_add.
+__device__ __noinline__ void coop_dbl(CoopArr& out, const CoopArr& A, bool active, CoopTmp& T, int warp, int lane) {
+  uint32_t (*V)[32] = T.t[0], (*XX)[32] = T.t[1], (*W)[32] = T.t[2], (*S)[32] = T.t[3], (*MM)[32] = T.t[4], (*WY)[32] = T.t[5];
+  bool inf = true;
+  if (active) {
+    uint32_t z = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) z |= A.w[2][i][lane];
+    inf = z == 0;
+  }
+  const bool live = active && !inf;
+  if (live) {
+    if (warp == 0) cst(V, lane, sqr(dbl(cld(A.w[1], lane))));
+    else if (warp == 1) cst(XX, lane, sqr(cld(A.w[0], lane)));
+  }
+  __syncthreads();
+  Fq keep = Fq::zero(), m = Fq::zero();
+  if (live) {
+    if (warp == 0) cst(W, lane, mul(dbl(cld(A.w[1], lane)), cld(V, lane)));
+    else if (warp == 1) cst(S, lane, mul(cld(A.w[0], lane), cld(V, lane)));
+    else if (warp == 2) { Fq xx = cld(XX, lane); m = add(dbl(xx), xx); cst(MM, lane, sqr(m)); }
+    else keep = mul(cld(V, lane), cld(A.w[2], lane));                 // zz3
+  }
+  __syncthreads();
+  if (live) {
+    if (warp == 0 || warp == 2) {
+      Fq s_ = cld(S, lane);
+      Fq x3 = sub(sub(cld(MM, lane), s_), s_);
+      if (warp == 0) keep = x3;
+      else keep = mul(m, sub(s_, x3));                                // y3a (warp 2 still holds m)
+    } else if (warp == 1) cst(WY, lane, mul(cld(W, lane), cld(A.w[1], lane)));
+    else { Fq zz3 = keep; (void)zz3; }
+  }
+  Fq zzz3 = Fq::zero();
+  if (live && warp == 3) zzz3 = mul(cld(W, lane), cld(A.w[3], lane));
+  __syncthreads();
+  if (live) {                                                         // infinity stays infinity (nothing to write when out == A)
+    if (warp == 0) cst(out.w[0], lane, keep);
+    else if (warp == 2) cst(out.w[1], lane, sub(keep, cld(WY, lane)));
+    else if (warp == 3) { cst(out.w[2], lane, keep); cst(out.w[3], lane, zzz3); }
+  } else if (active && &out != &A) {
+    cst(out.w[warp], lane, cld(A.w[warp], lane));
+  }
+  __syncthreads();
+}
+
+// Horner over the window groups of a plain (no precomputed windows) Pippenger MSM, one CTA of 128 threads per row:
+// acc = 2^c acc + G_w from the top window down.  The 255 dependent doublings are the latency floor of a one-off MSM
+// (a lone thread: ~9.6 us each = 2.5 ms, 70 % of a 2^16-point MSM); the four warps share each doubling / addition.
+__global__ void __launch_bounds__(128) k_msm_final_coop(const G1XYZZ* __restrict__ groups, int NG, int split, int c, G1Jac* __restrict__ out) {
+  __shared__ CoopArr ACC, OP;
+  __shared__ CoopTmp T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const G1XYZZ* g = groups + (size_t)blockIdx.x * NG * split;
+  auto field = [&](const G1XYZZ& p) -> Fq { return warp == 0 ? p.x : (warp == 1 ? p.y : (warp == 2 ? p.zz : p.zzz)); };
+  { G1XYZZ inf = xyzz_inf(); cst(ACC.w[warp], lane, field(inf)); }
+  __syncthreads();
+  const bool me = lane == 0;
+#pragma unroll 1
+  for (int w = NG - 1; w >= 0; --w) {
+    if (w != NG - 1)
+#pragma unroll 1
+      for (int d = 0; d < c; ++d) coop_dbl(ACC, ACC, me, T, warp, lane);
+#pragma unroll 1
+    for (int j = 0; j < split; ++j) {
+      if (me) cst(OP.w[warp], 0, field(g[(size_t)w * split + j]));
+      __syncthreads();
+      coop_add(ACC, ACC, lane, OP, lane, me, T, warp, lane);
+    }
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = xyzz_to_jac(cld_pt(ACC, 0));
+}
+
 // One CTA of 128 threads per row of K = 128 buckets: slot t owns buckets 4t..4t+3.
 //   A  running sums: run_t = sum of the slot's buckets, tot_t = their sum with weights 1..4        (6 additions)
 //   B  E_t = inclusive suffix sum of run over the slots, in place                                    (5)
@@ -790,7 +864,9 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
     }
     if ((rc = groups.alloc(sizeof(G1XYZZ) * ngroups, st))) return rc;
     ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce_scan<false><<<(unsigned)ngroups, T, 0, st>>>(buckets.as<G1XYZZ>(), cfg.K, groups.as<G1XYZZ>(), nullptr));
-    ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, 1, cfg.c, out));
+    static const bool no_coop_f = getenv("ZKDL_MSM_NO_COOP") != nullptr;
+    if (m <= 64 && !no_coop_f) ZK_LAUNCH(k_msm_final_coop<<<(unsigned)m, 128, 0, st>>>(groups.as<G1XYZZ>(), cfg.NG, 1, cfg.c, out));
+    else ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, 1, cfg.c, out));
     return ZK_OK;
   }
   // many buckets per group (plain Pippenger with wide windows): up to 256-thread CTAs, RL (8) buckets per thread, more only
@@ -801,7 +877,9 @@ int msm_run(const zkdl_g1_table* t, const Fr* scalars, size_t m, int mont, int c
   int split = cfg.K / (T * RL); if (split < 1) split = 1; if (split > 16) split = 16;
   if ((rc = groups.alloc(sizeof(G1XYZZ) * m * cfg.NG * split, st))) return rc;
   ZK_LAUNCH_P(st, 0.0, 0.0, 0.0, k_msm_reduce<<<(unsigned)(m * cfg.NG * split), T, sizeof(G1XYZZ) * T, st>>>(buckets.as<G1XYZZ>(), cfg.K, split, groups.as<G1XYZZ>()));
-  ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, split, cfg.c, out));
+  static const bool no_coop_final = getenv("ZKDL_MSM_NO_COOP") != nullptr;
+  if (m <= 64 && !no_coop_final) ZK_LAUNCH(k_msm_final_coop<<<(unsigned)m, 128, 0, st>>>(groups.as<G1XYZZ>(), cfg.NG, split, cfg.c, out));   // few rows: latency
+  else ZK_LAUNCH(k_msm_final<<<div_up(m, 64), 64, 0, st>>>(groups.as<G1XYZZ>(), m, cfg.NG, split, cfg.c, out));
   return ZK_OK;
 }
 
@@ -951,17 +1029,18 @@ int zkdl_g1_me(const zkdl_g1_jacobian_t* a, size_t n, const zkdl_fr_t* u_host, s
   ZK_REQUIRE(k < 31, ZK_ERR_DIM, "Incompatible dimensions");
   if (k == 0) { ZK_REQUIRE(n == 1, ZK_ERR_DIM, "Incompatible dimensions"); ZK_CUDA(cudaMemcpyAsync(out, a, sizeof(G1Jac), cudaMemcpyDeviceToDevice, st)); return ZK_OK; }
   ZK_REQUIRE(!(n <= ((size_t)1 << (k - 1)) || n > ((size_t)1 << k)), ZK_ERR_DIM, "Incompatible dimensions");   // g1-tensor.cu:488
-  zkdl_g1_table* tab = nullptr;
-  int rc = zkdl_g1_table_create(a, n, 0, 0, &tab, stream); if (rc) return rc;
-  Scratch uq, E;
-  if ((rc = uq.alloc(sizeof(Fr) * k, st))) { zkdl_g1_table_destroy(tab); return rc; }
-  cudaMemcpyAsync(uq.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st);
-  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << k), st))) { zkdl_g1_table_destroy(tab); return rc; }
-  rc = build_eq_table(uq.as<Fr>(), u_host, (int)k, 0, E.as<Fr>(), st);
-  if (!rc) rc = msm_run(tab, E.as<Fr>(), 1, 1, 0, reinterpret_cast<G1Jac*>(out), st);
-  cudaStreamSynchronize(st);                     // the temporary table must outlive the kernels
-  zkdl_g1_table_destroy(tab);
-  return rc;
+  // a one-shot (plain Pippenger) base table in stream-ordered scratch memory: no cudaMalloc, no host synchronisation
+  Scratch tmp, pts, uq, E; int rc;
+  if ((rc = tmp.alloc(sizeof(G1XYZZ) * n, st))) return rc;
+  if ((rc = pts.alloc(sizeof(G1Affine) * n, st))) return rc;
+  ZK_LAUNCH(k_table_expand<<<div_up(n, G1_THREADS), G1_THREADS, 0, st>>>(reinterpret_cast<const G1Jac*>(a), n, 1, tmp.as<G1XYZZ>()));
+  ZK_LAUNCH(k_batch_affine<<<div_up(div_up(n, INV_CH), G1_THREADS), G1_THREADS, 0, st>>>(tmp.as<G1XYZZ>(), pts.as<G1Affine>(), n));
+  zkdl_g1_table tab; tab.n = n; tab.full = 0; tab.windows = 1; tab.pts = pts.as<G1Affine>(); tab.bytes = sizeof(G1Affine) * n;
+  if ((rc = uq.alloc(sizeof(Fr) * k, st))) return rc;
+  ZK_CUDA(cudaMemcpyAsync(uq.p, u_host, sizeof(Fr) * k, cudaMemcpyHostToDevice, st));
+  if ((rc = E.alloc(sizeof(Fr) * ((size_t)1 << k), st))) return rc;
+  if ((rc = build_eq_table(uq.as<Fr>(), u_host, (int)k, 0, E.as<Fr>(), st))) return rc;
+  return msm_run(&tab, E.as<Fr>(), 1, 1, 0, reinterpret_cast<G1Jac*>(out), st);
 }
 
 }  // extern "C"
