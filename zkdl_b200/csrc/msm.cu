@@ -7,12 +7,15 @@
 // Design.  A Commitment is a fixed generator set, so zkdl_g1_table_create precomputes affine window
 // tables 2^(4w) G[i] once; every commitment, opening round and commitment-vector evaluation is then a batched
 // Pippenger MSM over those tables with NO doublings on the proving path:
-//   count  : signed-digit recode every scalar (digit width c = 4t), histogram (row, bucket) keys
-//   scan   : exclusive prefix sum of the histogram
+//   count  : signed-digit recode every scalar (digit width c = 4t; c = 8 with tables: 128 buckets per row), histogram (row, bucket) keys
+//   scan   : exclusive prefix sums (bucket offsets, partial slots) + chunk plan; ONE single-CTA launch on the few-keys path
 //   scatter: counting sort of (window-table index, sign) entries by key
-//   accum  : S lanes per bucket, XYZZ += affine mixed additions (8M+2S), warp-shuffle combine of the S partials
-//   reduce : one CTA per (row, window-group): sum_k k*B_k by per-thread running sums + shared-memory tree
-//   final  : Horner over window groups (plain mode only) and XYZZ -> Jacobian
+//   accum  : the sorted list cut into equal chunks, one per thread: XYZZ += affine mixed additions (8M+2S), one partial per
+//            (chunk, bucket); combine: G lanes per bucket add the partials up
+//   reduce : sum_k k*B_k per (row, window-group).  Few rows: k_msm_reduce_coop, four warps share every point addition
+//            (one Fq product each per dependency level); many rows: k_msm_reduce_scan (shuffle suffix scan + tree);
+//            wide windows (plain Pippenger): k_msm_reduce (running sums + shared-memory scan)
+//   final  : Horner over window groups (plain mode only; cooperative doublings for few rows) and XYZZ -> Jacobian
 // me_open's log|G| dependent folding rounds are re-expressed as 3*log|G|+1 independent MSMs over the ORIGINAL
 // generators (k_open_scalars computes the per-round scalars), so a whole opening is ONE batched MSM.
 #include <atomic>

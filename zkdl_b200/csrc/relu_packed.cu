@@ -6,12 +6,13 @@
 // The cells are exactly Scalar_ONE / Scalar_ZERO, so the same proof elements can be produced from 48 bits per element:
 //   * rounds 0..2 of the binary sumcheck only ever see tables whose entries are functions of 2 / 4 / 8 original bits.
 //     With eq(u[j+1:], g) = eq_lo(j, group-in-element) * eq_hi(element), round j's three coefficients are
-//     sum_elem eq_hi[elem] * sum_groups LUT_j[group][bit pattern], i.e. table look-ups + additions and 7 products per
-//     ELEMENT for all three rounds together, instead of 6 products per CELL PAIR per round.
+//     sum_elem eq_hi[elem] * sum_groups LUT_j[group][bit pattern], i.e. table look-ups + additions and 5 products per
+//     ELEMENT for all three rounds together (only c1 and c2 are summed: c0 follows from the running claim, which starts
+//     at 0 for 0/1 cells - k_bin_packed_finish), instead of 6 products per CELL PAIR per round.
 //   * after three rounds each table entry is V3[byte]: round 3 pairs two of them, i.e. its coefficients are a function
 //     of 16 bits (a 65536-entry look-up table in L2, pre-weighted by the in-element eq factor), and the table after
-//     round 3 is V4[16-bit half].  For mag_bin (32 cells) round 4 pairs the two halves of an element: 6 products per
-//     ELEMENT.  k_bin_r34 does these rounds straight from the packed words and writes the folded table with ONE entry
+//     round 3 is V4[16-bit half].  For mag_bin (32 cells) round 4 pairs the two halves of an element: 2 + 4 products per
+//     ELEMENT for rounds 3 and 4.  k_bin_r34 does these rounds straight from the packed words and writes the folded table with ONE entry
 //     per element (a^(5) for mag_bin, a^(4) for rem_bin); only then do the generic single-pass rounds (fr_kernels.cu)
 //     take over.  The tables a^(3), a^(4) (8 and 4 entries per element) are never materialised.
 //   * mag_bin.partial_me(u, 32) / rem_bin.partial_me(u, 16) (zkrelu.cu:92,94) are per-bit sums of eq(u, elem).
