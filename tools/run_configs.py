@@ -81,3 +81,22 @@ if "fs" in args:                                      # Fiat-Shamir mode of the 
     t0 = time.time(); ok = fs.verify_all(public, P.B, proofs); t_verify = time.time() - t0
     print(json.dumps({"config": "demo MLP 18.2M params, batch 256, Fiat-Shamir mode (device-side transcript, reference Fr tables, layers sequential)",
                       "prove_ms": t_prove * 1e3, "verify_s": t_verify, "verified": bool(ok)}))
+if "linked" in args:                                  # linked mode of the demo MLP: one chained proof, auxiliary tables committed and opened
+    from zkdl_b200 import linked
+    ws, x = mlp.synthetic_mlp(mlp.demo_layer_dims(), 256, seed=0)
+    P = mlp.MLPProver(ws, gen_seed=1)
+    P.forward(x); P.check_range()
+    linked.prove(P)
+    torch.cuda.synchronize(); t0 = time.time()
+    public, proof = linked.prove(P)
+    torch.cuda.synchronize(); t_prove = time.time() - t0
+    t0 = time.time(); aux = [linked._Aux(P, j) for j in range(len(P.layers) - 1)]; torch.cuda.synchronize(); t_aux = time.time() - t0
+    del aux
+    t0 = time.time(); ok = linked.verify_linked(public, proof); t_verify = time.time() - t0
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "linked.zkp")
+    t0 = time.time(); nbytes = linked.export(public, proof, path); t_export = time.time() - t0
+    t0 = time.time(); ok2 = linked.verify_file(path); t_file = time.time() - t0
+    print(json.dumps({"config": "demo MLP 18.2M params, batch 256, linked mode (one chained Fiat-Shamir proof; sign / mag_bin / rem_bin committed, 6 openings per zkReLU)",
+                      "prove_ms": t_prove * 1e3, "of_which_aux_expand_commit_ms": t_aux * 1e3, "verify_s": t_verify, "verified": bool(ok),
+                      "file_bytes": nbytes, "export_s": t_export, "load_and_verify_s": t_file, "file_verified": bool(ok2),
+                      "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))

@@ -1,6 +1,6 @@
 """prove -> file -> verify for the demo path (the reference drops its proofs and has no verifier).
 
-    python -m zkdl_b200.proof_file prove  --out proof.zkp [--model traced_model.pt --input sample_input.pt] [--seed N]
+    python -m zkdl_b200.proof_file prove  --out proof.zkp [--model traced_model.pt --input sample_input.pt] [--seed N] [--fiat-shamir | --linked]
     python -m zkdl_b200.proof_file verify proof.zkp
 
 `prove` mirrors ./demo (demo.cu:99-143: load the TorchScript MLP and the input batch, commit, forward, prove) and writes
@@ -138,6 +138,7 @@ def main(argv=None):
     pp = sub.add_parser("prove"); pp.add_argument("--out", required=True); pp.add_argument("--model"); pp.add_argument("--input")
     pp.add_argument("--seed", type=int, default=0); pp.add_argument("--batch", type=int, default=256)
     pp.add_argument("--fiat-shamir", action="store_true", help="derive every challenge from a SHA-256 transcript (zkdl_b200/fiat_shamir.py) instead of seeded random_vec streams")
+    pp.add_argument("--linked", action="store_true", help="one chained Fiat-Shamir proof from the public output down to the public input, with committed and opened ReLU auxiliary tables (zkdl_b200/linked.py)")
     pv = sub.add_parser("verify"); pv.add_argument("file")
     a = ap.parse_args(argv)
     import torch
@@ -152,7 +153,15 @@ def main(argv=None):
             ws, x = mlp.synthetic_mlp(mlp.demo_layer_dims(), a.batch, seed=0)
         P = mlp.MLPProver(ws, gen_seed=a.seed + 1)
         P.forward(x)
-        if a.fiat_shamir:
+        if a.linked:
+            from . import linked
+            P.check_range()
+            torch.cuda.synchronize(); t0 = time.time()
+            pub, proof = linked.prove(P)
+            torch.cuda.synchronize(); dt = time.time() - t0
+            n = linked.export(pub, proof, a.out)
+            proof = proof["steps"]
+        elif a.fiat_shamir:
             from . import fiat_shamir
             fiat_shamir.prove(P)                                         # warm-up
             torch.cuda.synchronize(); t0 = time.time()
@@ -169,6 +178,14 @@ def main(argv=None):
         print(f"Proof time: {dt / x.shape[0]} seconds per data point.  {len(proof)} layer proofs, {n} bytes -> {a.out}")
     else:
         t0 = time.time()
+        with open(a.file, "rb") as f:
+            head = f.read(12)
+        if len(head) == 12 and head[:8] == serialize.MAGIC and int.from_bytes(head[8:], "little") == 3:
+            from . import linked
+            linked.verify_file(a.file)
+            print(f"verified in {time.time() - t0:.2f} s: the public output is the quantised MLP of the public input under the committed weights "
+                  "[one chained Fiat-Shamir transcript; ReLU auxiliary tables committed and opened: see zkdl_b200/linked.py for what the reference's opening leaves open]")
+            return 0
         s = verify_file(a.file)
         print(f"transcript self-consistent: {len(s)} layer proofs (every expected one, once) checked in {time.time() - t0:.2f} s: "
               + ", ".join(f"{k}{i}" for k, i, _ in s) + "  [injected challenges, per-layer claims unlinked: see the module docstring]")

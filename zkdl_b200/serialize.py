@@ -26,23 +26,16 @@ MAGIC = b"ZKDLPRF1"
 
 
 def _ints(rows):
-    rows = np.ascontiguousarray(rows, dtype=np.uint32)
-    w = rows.shape[-1]
-    out = []
-    for r in rows.reshape(-1, w):
-        v = 0
-        for j in range(w - 1, -1, -1):
-            v = (v << 32) | int(r[j])
-        out.append(v)
-    return out
+    rows = np.ascontiguousarray(rows, dtype="<u4")
+    n = 4 * rows.shape[-1]
+    b = rows.tobytes()                                                  # little-endian limbs, low limb first = the integer's bytes
+    return [int.from_bytes(b[i:i + n], "little") for i in range(0, len(b), n)]
 
 
 def _limbs(vals, w):
-    out = np.zeros((len(vals), w), dtype=np.uint32)
-    for i, v in enumerate(vals):
-        for j in range(w):
-            out[i, j] = (v >> (32 * j)) & 0xFFFFFFFF
-    return out
+    if not len(vals):
+        return np.zeros((0, w), dtype=np.uint32)
+    return np.frombuffer(b"".join(int(v).to_bytes(4 * w, "little") for v in vals), dtype="<u4").reshape(-1, w).astype(np.uint32)
 
 
 # ------------------------------------------------------------------------------------------------ Fr
@@ -156,16 +149,25 @@ def _u32(*v):
     return struct.pack("<%dI" % len(v), *v)
 
 
-def dumps(public, tasks, fiat_shamir=False):
+def dumps(public, tasks, fiat_shamir=False, linked=None):
     """public: [{in_dim, out_dim, I, O, generators [n,36] normalised, commitment [m,36] normalised}] per layer;
     tasks: [{kind: "fc"|"relu", layer, challenges: [[k,8] limbs ...], fr: [r,8] limbs, g1: [s,36] normalised or None}]
     in proving order; batch is stored in the header.  Version 1 = injected challenges (stored per task); version 2 =
-    Fiat-Shamir mode (zkdl_b200/fiat_shamir.py): same layout, every task's challenge list is empty - the verifier derives them."""
-    out = [MAGIC, _u32(2 if fiat_shamir else 1, len(public["layers"]), public["batch"])]
+    Fiat-Shamir mode (zkdl_b200/fiat_shamir.py): same layout, every task's challenge list is empty - the verifier derives them.
+    Version 3 = linked mode (zkdl_b200/linked.py): version 2 plus, after the public part, the input and output tables and the
+    three auxiliary row commitments (sign, mag_bin, rem_bin) of every zkReLU layer; linked = {"input", "output", "aux_com"}."""
+    out = [MAGIC, _u32(3 if linked is not None else 2 if fiat_shamir else 1, len(public["layers"]), public["batch"])]
     for L in public["layers"]:
         out.append(_u32(L["in_dim"], L["out_dim"], L["I"], L["O"], len(L["generators"]), len(L["commitment"])))
         out.append(g1_uncompressed(L["generators"]))
         out.append(g1_compress(L["commitment"]))
+    if linked is not None:
+        for key in ("input", "output"):
+            out.append(_u32(len(linked[key]))); out.append(fr_to_bytes(linked[key]))
+        out.append(_u32(len(linked["aux_com"])))
+        for coms in linked["aux_com"]:
+            for c in coms:
+                out.append(_u32(len(c))); out.append(g1_compress(c))
     out.append(_u32(len(tasks)))
     for t in tasks:
         out.append(_u32(0 if t["kind"] == "fc" else 1, t["layer"], len(t["challenges"])))
@@ -200,13 +202,17 @@ def loads(buf):
     if r.take(8) != MAGIC:
         raise ValueError("not a zkdl_b200 proof file")
     version, nl, batch = r.u32(3)
-    if version not in (1, 2):
+    if version not in (1, 2, 3):
         raise ValueError("unsupported proof file version %d" % version)
     layers = []
     for _ in range(nl):
         in_dim, out_dim, I, O, ng, nc = r.u32(6)
         layers.append({"in_dim": in_dim, "out_dim": out_dim, "I": I, "O": O,
                        "generators": g1_from_uncompressed(r.take(96 * ng)), "commitment": g1_decompress(r.take(48 * nc))})
+    linked = None
+    if version == 3:
+        linked = {"input": fr_from_bytes(r.take(32 * r.u32())), "output": fr_from_bytes(r.take(32 * r.u32()))}
+        linked["aux_com"] = [[g1_decompress(r.take(48 * r.u32())) for _ in range(3)] for _ in range(r.u32())]
     tasks = []
     for _ in range(r.u32()):
         kind, layer, nch = r.u32(3)
@@ -219,6 +225,6 @@ def loads(buf):
                       "g1": g1_decompress(r.take(48 * ng1)) if ng1 else None})
     if r.o != len(buf):
         raise ValueError("trailing bytes after the last task")
-    if version == 2 and any(t["challenges"] for t in tasks):
+    if version >= 2 and any(t["challenges"] for t in tasks):
         raise ValueError("a Fiat-Shamir proof file must not carry challenges")
-    return {"batch": batch, "layers": layers, "fiat_shamir": version == 2}, tasks
+    return {"batch": batch, "layers": layers, "fiat_shamir": version == 2, "linked": linked}, tasks
