@@ -76,3 +76,31 @@ def test_linked_batch_one_pads_short_tables(cpu_zk):
     public, proof = linked.prove(P, check=True)
     assert [c.shape[0] for c in proof["aux_com"][0]] == [1, 16, 8]
     assert linked.verify_linked(public, proof)
+
+
+def test_linked_magnitude_range(cpu_zk):
+    """Tiny pre-activations: -2^15 <= Z < 0 rounds the magnitude UP to exactly 2^31 (bit 31 set, low bits clear), which the
+    range sumcheck b31 o low31 = 0 accepts; the other decomposition of a positive Z, (sign 0, M + 2^31), which would zero
+    an activation, is rejected by it."""
+    P = mock.ToyProver([(6, 8), (8, 4)], batch=2, seed=11, weight_scale=1e-4, input_scale=1e-3)
+    magp = P.aux[0][1].numpy().view(np.uint32)
+    assert (magp == 1 << 31).any(), "the toy case should contain a rounded-up tiny negative"
+    public, proof = linked.prove(P, check=True)
+    assert linked.verify_linked(public, proof)
+    # the cheat: entry e is positive with a small magnitude; claim it negative with M + 2^31 and output 0
+    P = mock.ToyProver([(6, 8), (8, 4)], batch=2, seed=12)
+    sign, magp, remp = P.aux[0]
+    sg = mock.to_host(sign).copy()
+    m = magp.numpy().view(np.uint32).copy()
+    e = int(np.flatnonzero(sg.any(axis=1) & (m > 0) & (m < (1 << 31)))[0])
+    sg[e] = 0
+    m[e] += 1 << 31
+    a = mock.to_host(P.A[0]).copy()
+    a[e] = 0
+    import torch
+    P.aux[0] = (mock.to_device(sg), torch.from_numpy(m.view(np.int32).copy()), remp)
+    P.A[0] = mock.to_device(a)
+    P.Z[1] = mock.to_device(mock.orc.fr_matmul(a, mock.to_host(P.layers[1].W), P.B, P.layers[1].I, P.layers[1].O))
+    public, proof = linked.prove(P, check=True)                           # every link holds: the decomposition is consistent
+    with pytest.raises(verify.VerifyError, match="sumcheck: round 0"):
+        linked.verify_linked(public, proof)

@@ -69,8 +69,13 @@ def test_chain_equals_the_oracle(chain, monkeypatch):
     for mod in (fiat_shamir, linked, verify):
         monkeypatch.setattr(mod, "zk", mock)
     pub_o, proof_o = linked.prove(H, check=True)
+    def canon(pts):                                                        # infinity has many limb images (z = 0)
+        a = np.array(pts, dtype=np.uint32).reshape(-1, 36)
+        a[(a[:, 24:] == 0).all(axis=1)] = 0
+        return a
+
     for a, b in zip(public, pub_o):
-        assert np.array_equal(a["generators"], b["generators"]) and np.array_equal(a["commitment"], b["commitment"])
+        assert np.array_equal(canon(a["generators"]), canon(b["generators"])) and np.array_equal(canon(a["commitment"]), canon(b["commitment"]))
     for ca, cb in zip(proof["aux_com"], proof_o["aux_com"]):
         for x, y in zip(ca, cb):
             assert np.array_equal(x, y), "auxiliary commitments differ from the oracle's"

@@ -142,7 +142,7 @@ class _Layer:
 
 
 class ToyProver:
-    def __init__(self, dims, batch, seed=0):
+    def __init__(self, dims, batch, seed=0, weight_scale=1.0, input_scale=1.0):
         rng = np.random.default_rng(seed)
         gen = orc.g1_generator()
         B = 1 << max(0, (batch - 1).bit_length())
@@ -155,16 +155,24 @@ class ToyProver:
             sc = orc.to_limbs([int(v) for v in rng.integers(1, 1 << 62, L.ngens)])
             L.G = to_device(orc.g1_mul(gen, sc, fast=True))
             L.gens = G1Table(L.G)
-            w = ((rng.random((i_dim, o_dim)) * 2 - 1) / np.sqrt(i_dim)).astype(np.float32)
+            w = ((rng.random((i_dim, o_dim)) * 2 - 1) / np.sqrt(i_dim) * weight_scale).astype(np.float32)
             L.W = to_device(orc.fr_mont(orc.float_to_fr(w, L.I, L.O)))
             L.com = commit(L.gens, L.W)
             L.com_table = G1Table(L.com)
             self.layers.append(L)
-        x = rng.standard_normal((batch, dims[0][0])).astype(np.float32)
+        x = (rng.standard_normal((batch, dims[0][0])) * input_scale).astype(np.float32)
         self.X = to_device(orc.fr_mont(orc.float_to_fr(x, B, self.layers[0].I)))
-        self.Z, self.A, self.aux = [], [], []
-        cur = to_host(self.X)
+        self.forward_from(0, to_host(self.X))
+
+    def forward_from(self, first, cur):
+        """(Re)computes layers first.. from the activation table `cur` (numpy limbs)."""
+        if first == 0:
+            self.Z, self.A, self.aux = [], [], []
+        del self.Z[first:], self.A[first:], self.aux[first:]
+        B = self.B
         for i, L in enumerate(self.layers):
+            if i < first:
+                continue
             z = orc.fr_matmul(cur, to_host(L.W), B, L.I, L.O)
             self.Z.append(to_device(z))
             if i + 1 < len(self.layers):

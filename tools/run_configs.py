@@ -96,7 +96,7 @@ if "linked" in args:                                  # linked mode of the demo 
     path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "linked.zkp")
     t0 = time.time(); nbytes = linked.export(public, proof, path); t_export = time.time() - t0
     t0 = time.time(); ok2 = linked.verify_file(path); t_file = time.time() - t0
-    print(json.dumps({"config": "demo MLP 18.2M params, batch 256, linked mode (one chained Fiat-Shamir proof; sign / mag_bin / rem_bin committed, 6 openings per zkReLU)",
+    print(json.dumps({"config": "demo MLP 18.2M params, batch 256, linked mode (one chained Fiat-Shamir proof; sign / mag_bin / rem_bin committed, 7 openings per zkReLU, magnitude range sumcheck)",
                       "prove_ms": t_prove * 1e3, "of_which_aux_expand_commit_ms": t_aux * 1e3, "verify_s": t_verify, "verified": bool(ok),
                       "file_bytes": nbytes, "export_s": t_export, "load_and_verify_s": t_file, "file_verified": bool(ok2),
                       "mem_GB": torch.cuda.max_memory_allocated() / 1e9}))

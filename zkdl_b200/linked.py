@@ -15,12 +15,17 @@ Chain, from the output backwards (r = evaluation point over (out, batch) index b
     zkReLU X_i = A_{i-1} = M o sign  (zkrelu.cu:41):  sum_x eq(p, x) M(x) sign(x) = a   Hadamard sumcheck with the eq
            point p = (u_in, u_bs)  ->  M~(q), sign~(q) at the fold point q
            recover rows at q (the reference takes them at an unrelated point): mag_bin~(k, q), rem_bin~(k, q);
-           M~(q) = sum_k 2^k mag_bin~(k, q), rem~(q) = sum_{k<15} 2^k rem_bin~(k, q) - 2^15 rem_bin~(15, q), bit plane 31 of
-           the magnitude must vanish (so that sign is determined by Z: |Z| < 2^47)
+           M~(q) = sum_k 2^k mag_bin~(k, q), rem~(q) = sum_{k<15} 2^k rem_bin~(k, q) - 2^15 rem_bin~(15, q)
            Z_{i-1}~(q) = 2^16 M~(q) + rem~(q) - 2^47 (1 - sign~(q))     (relu_kernel's decomposition)  -> next claim, r = q
            binary sumchecks on mag_bin, rem_bin AND sign (the reference has none for sign)
-           openings against the auxiliary commitments: mag_bin at (tau_m, q) and at its binary sumcheck's fold point, rem_bin
-           likewise, sign at q and at its fold point (tau_m, tau_r: transcript points batching the 32 / 16 recover rows)
+           range of the magnitude: relu_kernel's M lies in [0, 2^31] (2^31 itself for -2^15 <= Z < 0, rounded up), but 32 bits
+           hold twice that, and (sign, M) / (1 - sign, M + 2^31) would decompose the same Z with different outputs.  So
+           M <= 2^31 is proved as  b31(x) * low31(x) = 0  for all x:  sum_x eq(t, x) b31(x) low31(x) = 0, a Hadamard sumcheck
+           at a transcript point t, ending in b31~(q2), low31~(q2), which a second set of recover rows at q2 gives.  With it
+           the decomposition is unique except Z in [-2^15, 2^15), where both forms give the output 0.
+           openings against the auxiliary commitments: mag_bin at (tau_m, q), at (tau_2, q2) and at its binary sumcheck's fold
+           point, rem_bin at (tau_r, q) and at its fold point, sign at q and at its fold point (tau_*: transcript points
+           batching the 32 / 16 recover rows into one evaluation)
 The transcript is seeded with the public model, the input, the output and the auxiliary commitments, so every challenge
 depends on all of them.  Not covered: the reference's opening folds with the coordinates of the evaluation point
 (commitment.cu:43-81) - it is kept as is."""
@@ -34,6 +39,7 @@ from . import verify
 from .verify import P as MOD, plain, _req
 
 Q_BITS, R_BITS = 32, 16                               # zkrelu.cu:73-76
+N_OPENS = 7                                           # openings per zkReLU step
 
 
 def _clog(v):
@@ -96,6 +102,10 @@ class _Aux:
         m = torch.zeros((magp.shape[0], 8), dtype=torch.int32, device=magp.device)
         m[:, 0] = magp                                                      # the packed magnitude IS mag_rescaled (zkrelu.cu:31)
         self.M = zk.fr_elementwise(zk.OP_MONT, m, out=m)
+        lo, top = torch.zeros_like(m), torch.zeros_like(m)
+        lo[:, 0] = magp & 0x7FFFFFFF                                        # low31 and b31 of the same integers
+        top[:, 0] = (magp >> 31) & 1
+        self.low, self.top = zk.fr_elementwise(zk.OP_MONT, lo, out=lo), zk.fr_elementwise(zk.OP_MONT, top, out=top)
         self.tables = [_pad_table(t, L.ngens) for t in (self.sign, self.mag, self.rem)]
         self.com = [zk.commit(L.gens, t) for t in self.tables]             # unmont(0/1) = 0/1: one-digit scalars
         self.com_host = [_canon_g1(c) for c in self.com]
@@ -170,14 +180,20 @@ def prove(P, check=False):
         p_sign, v_s, T.s = zk.sumcheck_fs(zk.FS_BIN, A.sign, None, u_s, Lg, T.s)
         p_sign, v_s = zk.to_host(p_sign).copy(), zk.to_host(v_s).copy()
         T.absorb_fr(p_sign[-1:])
-        tau_m, tau_r = T.vector(5), T.vector(4)
+        t2 = T.vector(Lg)                                                    # M <= 2^31:  b31 o low31 = 0
+        top, q2, T.s = zk.sumcheck_fs(zk.FS_HP, A.top, A.low, t2, Lg, T.s)
+        top, q2 = zk.to_host(top).copy(), zk.to_host(q2).copy()
+        T.absorb_fr(top[3 * Lg:])
+        r_top = zk.to_host(zk.fr_partial_me(A.mag, q2, Q_BITS)).copy()
+        T.absorb_fr(r_top)
+        tau_m, tau_r, tau_2 = T.vector(5), T.vector(4), T.vector(5)
         t_sign, t_mag, t_rem = A.tables
         c_sign, c_mag, c_rem = A.com
         opens = [_open(Lj, t_mag, c_mag, _cat(tau_m, q)), _open(Lj, t_mag, c_mag, v_z),
                  _open(Lj, t_rem, c_rem, _cat(tau_r, q)), _open(Lj, t_rem, c_rem, v_r),
-                 _open(Lj, t_sign, c_sign, q), _open(Lj, t_sign, c_sign, v_s)]
-        steps.append({"kind": "relu", "layer": j, "hp": hp, "r_mag": r_mag, "r_rem": r_rem,
-                      "bin_mag": p_mag, "bin_rem": p_rem, "bin_sign": p_sign, "opens": opens})
+                 _open(Lj, t_sign, c_sign, q), _open(Lj, t_sign, c_sign, v_s), _open(Lj, t_mag, c_mag, _cat(tau_2, q2))]
+        steps.append({"kind": "relu", "layer": j, "hp": hp, "r_mag": r_mag, "r_rem": r_rem, "bin_mag": p_mag, "bin_rem": p_rem,
+                      "bin_sign": p_sign, "top": top, "r_top": r_top, "opens": opens})
         if check:
             Mq, sq = plain(hp[-2]), plain(hp[-1])
             remq = (sum(plain(r_rem[k]) << k for k in range(15)) - (plain(r_rem[15]) << 15)) % MOD
@@ -255,8 +271,10 @@ def verify_linked(public, proof):
             s = next(it)
             hp, r_mag, r_rem = (np.asarray(s[k], np.uint32) for k in ("hp", "r_mag", "r_rem"))
             p_mag, p_rem, p_sign = (np.asarray(s[k], np.uint32) for k in ("bin_mag", "bin_rem", "bin_sign"))
-            _req(hp.shape == (3 * Lg + 2, 8) and r_mag.shape == (Q_BITS, 8) and r_rem.shape == (R_BITS, 8), f"relu {j}: wrong lengths")
-            _req(len(s["opens"]) == 6, f"relu {j}: six openings expected")
+            top, r_top = np.asarray(s["top"], np.uint32), np.asarray(s["r_top"], np.uint32)
+            _req(hp.shape == (3 * Lg + 2, 8) and r_mag.shape == (Q_BITS, 8) and r_rem.shape == (R_BITS, 8)
+                 and top.shape == (3 * Lg + 2, 8) and r_top.shape == (Q_BITS, 8), f"relu {j}: wrong lengths")
+            _req(len(s["opens"]) == N_OPENS, f"relu {j}: {N_OPENS} openings expected")
             p = _cat(u_in, u_bs)
             q = T.rounds(hp, Lg)
             Mq, sq = verify.verify_weighted(hp, p, q, a0, 2, lambda c, f: c == f[0] * f[1] % MOD)
@@ -264,7 +282,6 @@ def verify_linked(public, proof):
             T.absorb_fr(r_mag); T.absorb_fr(r_rem)
             rm, rr = [plain(x) for x in r_mag], [plain(x) for x in r_rem]
             _req(sum(v << k for k, v in enumerate(rm)) % MOD == Mq, f"relu {j}: recover rows do not add up to the magnitude")
-            _req(rm[Q_BITS - 1] == 0, f"relu {j}: magnitude bit 31 must be zero")
             remq = (sum(rr[k] << k for k in range(R_BITS - 1)) - (rr[R_BITS - 1] << (R_BITS - 1))) % MOD
             u_z = T.vector(Lg + 5); v_z = T.rounds(p_mag, Lg + 5)
             f_mag = verify.verify_bin(p_mag, u_z, v_z)[0]
@@ -275,9 +292,17 @@ def verify_linked(public, proof):
             u_s = T.vector(Lg); v_s = T.rounds(p_sign, Lg)
             f_sign = verify.verify_bin(p_sign, u_s, v_s)[0]
             T.absorb_fr(p_sign[-1:])
-            tau_m, tau_r = T.vector(5), T.vector(4)
+            t2 = T.vector(Lg); q2 = T.rounds(top, Lg)
+            b31, low = verify.verify_weighted(top, t2, q2, 0, 2, lambda c, f: c == f[0] * f[1] % MOD)
+            T.absorb_fr(top[3 * Lg:])
+            T.absorb_fr(r_top)
+            rt = [plain(x) for x in r_top]
+            _req(rt[Q_BITS - 1] == b31 and sum(v << k for k, v in enumerate(rt[:Q_BITS - 1])) % MOD == low,
+                 f"relu {j}: second recover rows do not match the magnitude-range sumcheck")
+            tau_m, tau_r, tau_2 = T.vector(5), T.vector(4), T.vector(5)
             e_mag = sum(w * v for w, v in zip(_eq_weights(tau_m), rm)) % MOD
             e_rem = sum(w * v for w, v in zip(_eq_weights(tau_r), rr)) % MOD
+            e_top = sum(w * v for w, v in zip(_eq_weights(tau_2), rt)) % MOD
             c_sign, c_mag, c_rem = aux_dev[j]
             o = s["opens"]
             G, gt = gens[j], tabs[j]
@@ -287,6 +312,7 @@ def verify_linked(public, proof):
             _check_open(G, gt, c_rem, o[3], v_r, f_rem, f"relu {j} rem_bin at its sumcheck point")
             _check_open(G, gt, c_sign, o[4], q, sq, f"relu {j} sign at the recover point")
             _check_open(G, gt, c_sign, o[5], v_s, f_sign, f"relu {j} sign at its sumcheck point")
+            _check_open(G, gt, c_mag, o[6], _cat(tau_2, q2), e_top, f"relu {j} mag_bin at the range point")
             z = ((Mq << 16) + remq - (1 << 47) * (1 - sq)) % MOD                    # Z_j~(q): the next layer's claim
             r = q
     finally:
@@ -300,13 +326,14 @@ def verify_linked(public, proof):
 # ------------------------------------------------------------------------------------------------ wire format (serialize.py, version 3)
 def to_tasks(proof):
     """The chain as serialize.py task records: fc = [ip | open ret] + opening points, relu = [hp | recover rows | three binary
-    sumchecks | six open rets] + the six openings' points."""
+    sumchecks | range sumcheck | second recover rows | open rets] + the openings' points."""
     tasks = []
     for s in proof["steps"]:
         if s["kind"] == "fc":
             fr, g1 = _cat(s["ip"], s["open_w"]["ret"]), s["open_w"]["g1"]
         else:
-            fr = _cat(s["hp"], s["r_mag"], s["r_rem"], s["bin_mag"], s["bin_rem"], s["bin_sign"], *[o["ret"] for o in s["opens"]])
+            fr = _cat(s["hp"], s["r_mag"], s["r_rem"], s["bin_mag"], s["bin_rem"], s["bin_sign"], s["top"], s["r_top"],
+                      *[o["ret"] for o in s["opens"]])
             g1 = np.concatenate([o["g1"] for o in s["opens"]])
         tasks.append({"kind": s["kind"], "layer": s["layer"], "challenges": [], "fr": fr, "g1": g1})
     return tasks
@@ -326,12 +353,12 @@ def from_tasks(public, batch, extra, tasks):
             steps.append({"kind": "fc", "layer": t["layer"], "ip": fr[:3 * ki + 2], "open_w": {"ret": fr[3 * ki + 2:], "g1": g1}})
         else:
             Lg = _clog(batch * L["O"])
-            cuts = np.cumsum([3 * Lg + 2, Q_BITS, R_BITS, 3 * (Lg + 5) + 1, 3 * (Lg + 4) + 1, 3 * Lg + 1])
-            _req(len(fr) == cuts[-1] + 6 and len(g1) == 6 * (3 * g + 2), f"relu {t['layer']}: wrong number of proof elements")
-            hp, r_mag, r_rem, b_mag, b_rem, b_sign, rets = np.split(fr, cuts)
-            opens = [{"ret": rets[k:k + 1], "g1": g1[k * (3 * g + 2):(k + 1) * (3 * g + 2)]} for k in range(6)]
-            steps.append({"kind": "relu", "layer": t["layer"], "hp": hp, "r_mag": r_mag, "r_rem": r_rem,
-                          "bin_mag": b_mag, "bin_rem": b_rem, "bin_sign": b_sign, "opens": opens})
+            cuts = np.cumsum([3 * Lg + 2, Q_BITS, R_BITS, 3 * (Lg + 5) + 1, 3 * (Lg + 4) + 1, 3 * Lg + 1, 3 * Lg + 2, Q_BITS])
+            _req(len(fr) == cuts[-1] + N_OPENS and len(g1) == N_OPENS * (3 * g + 2), f"relu {t['layer']}: wrong number of proof elements")
+            hp, r_mag, r_rem, b_mag, b_rem, b_sign, top, r_top, rets = np.split(fr, cuts)
+            opens = [{"ret": rets[k:k + 1], "g1": g1[k * (3 * g + 2):(k + 1) * (3 * g + 2)]} for k in range(N_OPENS)]
+            steps.append({"kind": "relu", "layer": t["layer"], "hp": hp, "r_mag": r_mag, "r_rem": r_rem, "bin_mag": b_mag,
+                          "bin_rem": b_rem, "bin_sign": b_sign, "top": top, "r_top": r_top, "opens": opens})
     return {"batch": batch, "input": extra["input"], "output": extra["output"], "aux_com": extra["aux_com"], "steps": steps}
 
 
