@@ -16,7 +16,8 @@ challenge is "a value < p read as Montgomery form", the reference's own conventi
 Proof layout per layer = the reference's; the challenges are not part of the proof.
 What is bound: zkFC - (u_bs, u_out) to the public root; Z(u) is absorbed before the matmul sumcheck, whose fold challenges
 u_in are the evaluation point of the weight opening.  zkReLU - the eq points to the root, every fold challenge to the
-previous rounds, u_recover to both binary sumchecks.  The per-layer claims are still NOT chained to each other (§8f-3)."""
+previous rounds, u_recover to both binary sumchecks.  In this mode the per-layer claims are NOT chained to each other, as in the
+reference; zkdl_b200/linked.py builds the chained proof (§8f-3) on the same transcript and device-side hashing."""
 import hashlib
 
 import numpy as np

@@ -16,7 +16,10 @@ X~(u) are bound to nothing outside their own layer proof, the Hadamard sumcheck'
 `partial_me(u_recover, .)` rows are evaluations at a point unrelated to the binary sumchecks' fold point, so the
 mag/rem "recover" relation is not verifiable from these elements (they are only length-checked).  Challenges are the
 prover's injected random_vec streams, as in the reference (no Fiat-Shamir transcript).  The result is therefore
-"transcript self-consistency", not soundness against a prover who picks its own challenges."""
+"transcript self-consistency", not soundness against a prover who picks its own challenges.
+`prove --fiat-shamir` removes the last point (challenges from a transcript), `prove --linked` also the first: it writes ONE
+chained proof (zkdl_b200/linked.py, file version 3) in which Z(u), X~(u), the recover rows and the auxiliary tables are all
+bound, and `verify` reports "verified" for it."""
 import argparse
 import sys
 import time
