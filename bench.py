@@ -316,9 +316,11 @@ def main():
         parts = parallel.gather_proof(flat, world, rank, "cuda", sizes=proof_sizes)   # proof elements of the other ranks' pieces -> rank 0
         return torch.cat(parts) if rank == 0 else flat
 
+    fwd_graph = os.environ.get("ZKDL_FORWARD_GRAPH", "1") != "0"
+
     def e2e_step(seed):
         xd = x_host.cuda(non_blocking=True)             # H2D of this step's input batch from pinned memory
-        P.forward(xd)                                   # quantised forward pass; every layer records an event ...
+        P.forward(xd, graph=fwd_graph)                  # quantised forward pass (replayed from CUDA graphs); every layer records an event ...
         flat = prove_step(seed, overlap_forward=True)   # ... and each piece waits only for its own layer's tables
         return flat.cpu()                               # D2H of the proof elements
 
@@ -533,6 +535,7 @@ def main():
     extra["commit_msm_mpts_s"] = (L2.I * L2.O) / (extra["commit_2048x2048_ms"] * 1e-3) / 1e6
     extra["setup_s"] = setup_s
     extra["forward_ms"] = timed(lambda: P.forward(x), reps=5, warm=1)
+    extra["forward_graph_ms"] = timed(lambda: P.forward(x, graph=True), reps=5, warm=2)
 
     cpu = None if (args.skip_cpu_baseline or world > 1) else cpu_baseline_sample()      # host baseline: rank 0 at N=1 only
     line = {"metric": METRIC, "value": ms / 1e3, "unit": "s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -478,9 +478,18 @@ def scratch_reserve(nbytes):
     _check(lib().zkdl_scratch_reserve(_sz(nbytes), _stream()))
 
 
+_scratch_gen = [0]
+
+
 def scratch_release_all():
-    """Frees the library's idle scratch arenas on the current device (zkdl_scratch_release_all; synchronises the device)."""
+    """Frees the library's idle scratch arenas on the current device (zkdl_scratch_release_all; synchronises the device).
+    CUDA graphs captured over library calls hold scratch addresses: scratch_generation() tells their owners to re-capture."""
+    _scratch_gen[0] += 1
     _check(lib().zkdl_scratch_release_all())
+
+
+def scratch_generation():
+    return _scratch_gen[0]
 
 
 def prof_enable(on=True):

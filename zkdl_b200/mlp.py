@@ -55,24 +55,69 @@ class MLPProver:
         self.n_params = sum(L.in_dim * L.out_dim for L in self.layers)
         torch.cuda.synchronize()
 
-    def forward(self, x):
-        """x: float32 CUDA [batch, in].  Keeps Z_i, A_i and the ReLU aux tables (demo.cu:23-38)."""
-        B = pad2(x.shape[0])
-        L0 = self.layers[0]
-        X = zk.float_to_fr(x.contiguous(), B, L0.I)                                          # zkfc.cu:106-115
-        self.X = zk.fr_elementwise(zk.OP_MONT, X, out=X)                                     # demo.cu:119
+    def forward(self, x, graph=False):
+        """x: float32 CUDA [batch, in].  Keeps Z_i, A_i and the ReLU aux tables (demo.cu:23-38).
+        graph=True replays the pass from CUDA graphs captured on the first call with this batch shape (one graph per layer,
+        so the per-layer events of prove(overlap_forward=True) stay): the ~65 small launches of a batch-256 pass are
+        launch-bound from Python (0.78 ms), the kernels themselves take a fraction of that.  The tables then live in the
+        graphs' memory pool and are OVERWRITTEN by the next forward(graph=True) call."""
         import torch
-        self.B = B
+        if graph:
+            return self._forward_graph(x)
+        self.B = pad2(x.shape[0])
         self.Z, self.A, self.aux, self.bad, self.ready = [], [], [], [], []
-        cur = self.X
-        for i, L in enumerate(self.layers):
-            z = zk.fr_matmul_prepared(cur, L.mm, B)
-            self.Z.append(z)
-            if i + 1 < len(self.layers):
-                a, sign, mag, rem, bad = zk.relu_packed(z)                                  # aux kept bit-packed
-                self.A.append(a); self.aux.append((sign, mag, rem)); self.bad.append(bad)
-                cur = a
+        cur = None
+        for i in range(len(self.layers)):
+            cur = self._forward_layer(i, x if i == 0 else cur)
             ev = torch.cuda.Event(); ev.record()                                            # layer i's tables are final here
+            self.ready.append(ev)
+        return self.Z[-1]
+
+    def _forward_layer(self, i, cur):
+        L = self.layers[i]
+        if i == 0:
+            X = zk.float_to_fr(cur.contiguous(), self.B, L.I)                                # zkfc.cu:106-115
+            self.X = cur = zk.fr_elementwise(zk.OP_MONT, X, out=X)                           # demo.cu:119
+        z = zk.fr_matmul_prepared(cur, L.mm, self.B)
+        self.Z.append(z)
+        if i + 1 < len(self.layers):
+            a, sign, mag, rem, bad = zk.relu_packed(z)                                      # aux kept bit-packed
+            self.A.append(a); self.aux.append((sign, mag, rem)); self.bad.append(bad)
+            return a
+        return z
+
+    def _forward_graph(self, x):
+        import torch
+        key = (tuple(x.shape), zk.scratch_generation())
+        main = torch.cuda.current_stream()
+        if getattr(self, "_fg_key", None) != key:
+            # Capture.  The library's scratch arenas are keyed by stream and grow with cudaMalloc, which a capture forbids:
+            # two eager passes on the capture stream size its arena first.  Scratch addresses are baked into the graphs, so
+            # the stream is reserved for them and zk.scratch_release_all() (which frees arenas) invalidates the capture.
+            self._fg_key, self._fg_graphs = None, []
+            st = self._fg_stream = getattr(self, "_fg_stream", None) or torch.cuda.Stream()
+            self._fg_x = torch.empty_like(x)
+            self._fg_x.copy_(x)
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                for _ in range(2):
+                    self.forward(self._fg_x)
+            st.synchronize()
+            self.B = pad2(x.shape[0])
+            self.Z, self.A, self.aux, self.bad = [], [], [], []
+            pool = torch.cuda.graph_pool_handle()
+            cur = None
+            for i in range(len(self.layers)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool, stream=st):
+                    cur = self._forward_layer(i, self._fg_x if i == 0 else cur)
+                self._fg_graphs.append(g)
+            self._fg_key = key
+        self._fg_x.copy_(x, non_blocking=True)
+        self.ready = []
+        for g in self._fg_graphs:
+            g.replay()
+            ev = torch.cuda.Event(); ev.record()
             self.ready.append(ev)
         return self.Z[-1]
 
