@@ -104,6 +104,12 @@ typedef struct zkdl_mm_weights zkdl_mm_weights;
 int zkdl_mm_weights_create(const zkdl_fr_t* W, size_t rows, size_t cols, zkdl_mm_weights** out, void* stream);
 int zkdl_mm_weights_destroy(zkdl_mm_weights* w);
 int zkdl_fr_matmul_prepared(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_mm_weights* prep, zkdl_fr_t* C, size_t rowsA, void* stream);
+/* One hidden layer of the forward pass, zkFC::operator() followed by zkReLU::operator() (demo.cu:30-34; zkfc.cu:117-126,
+ * zkrelu.cu:44-52): Z = A W, then act / sign / packed decomposition of Z as zkdl_relu_packed writes them.  On the tensor-core
+ * route the activation is applied to the exact integer accumulators in the product's epilogue; results are identical to
+ * zkdl_fr_matmul_prepared + zkdl_relu_packed. */
+int zkdl_fr_matmul_prepared_relu(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_mm_weights* prep, zkdl_fr_t* Z, size_t rowsA,
+                                 zkdl_fr_t* act, zkdl_fr_t* sign, uint32_t* mag_packed, uint16_t* rem_packed, uint32_t* out_of_range, void* stream);
 /* relu_kernel (zkrelu.cu:11-41): Z[n], sign[n], mag_bin[32n], rem_bin[16n].  Inputs outside +-2^47 (undefined in the
  * reference) give sign = 0, mag = 0 and are counted in *out_of_range (device u32, may be NULL). */
 int zkdl_relu(const zkdl_fr_t* X, zkdl_fr_t* Z, zkdl_fr_t* sign, zkdl_fr_t* mag_bin, zkdl_fr_t* rem_bin, size_t n, uint32_t* out_of_range, void* stream);

@@ -116,6 +116,24 @@ def test_quantise_and_relu_device_functions(hs):
     assert list(pos) == orc.fr_to_ints(sign)
 
 
+def test_short_to_mont_and_integer_relu(hs):
+    """to_mont_u64 (two CIOS rows against 2^320 mod p) == to_mont; relu_decompose_i64 == relu_decompose on the field image."""
+    ms = [0, 1, 2, (1 << 32) - 1, 1 << 32, (1 << 47) - 1, 1 << 47, (1 << 53) + 12345, (1 << 64) - 1] + [int(v) for v in rng.integers(0, 1 << 63, size=300)]
+    m = np.array(ms, dtype=np.uint64)
+    o = np.zeros((len(ms), 8), np.uint32)
+    hs.hs_to_mont_u64(p(m), p(o), C.c_size_t(len(ms)))
+    assert np.array_equal(o, orc.fr_from_ints(ms))
+    xs = [int(v) for v in rng.integers(-(1 << 46), 1 << 46, size=400)] + [0, 1, -1, 32767, 32768, -32768, -32769, 65535, 65536, (1 << 47) - 1, -(1 << 47), 1 << 47,
+                                                                           -(1 << 47) - 1, (1 << 53), -(1 << 53)]
+    n = len(xs)
+    v = np.array(xs, dtype=np.int64)
+    q, r = np.zeros(n, np.uint32), np.zeros(n, np.uint16); pos, bad = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    hs.hs_relu_i64(p(v), p(q), p(r), p(pos), p(bad), C.c_size_t(n))
+    q2, r2 = np.zeros(n, np.uint32), np.zeros(n, np.uint16); pos2, bad2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    hs.hs_relu(p(orc.fr_from_ints(xs)), p(q2), p(r2), p(pos2), p(bad2), C.c_size_t(n))
+    assert np.array_equal(q, q2) and np.array_equal(r, r2) and np.array_equal(pos, pos2) and np.array_equal(bad, bad2) and int(bad.sum()) == 4
+
+
 @pytest.mark.parametrize("c", [4, 8, 11, 12, 13, 16])
 def test_signed_digit_recoding(hs, c):
     W = (255 + c - 1) // c

@@ -284,6 +284,20 @@ def fr_matmul_prepared(A, weights, rows_a):
     return out
 
 
+def fr_matmul_prepared_relu(A, weights, rows_a):
+    """zkFC::operator() + zkReLU::operator() of one hidden layer: (Z, act, sign, packed mag, packed rem, out-of-range counter)."""
+    torch = _torch()
+    if A.shape[0] != rows_a * weights.rows:
+        raise DimensionError(1, "Incompatible dimensions")
+    n = rows_a * weights.cols
+    Z, act, sign = empty(n, 8), empty(n, 8), empty(n, 8)
+    mag = torch.empty(n, dtype=torch.int32, device="cuda"); rem = torch.empty(n, dtype=torch.int16, device="cuda")
+    bad = torch.empty(1, dtype=torch.int32, device="cuda")                     # zeroed by the library
+    _check(lib().zkdl_fr_matmul_prepared_relu(_ptr(A), _ptr(weights.W), weights.handle, _ptr(Z), _sz(rows_a), _ptr(act), _ptr(sign),
+                                              _ptr(mag), _ptr(rem), _ptr(bad), _stream()))
+    return Z, act, sign, mag, rem, bad
+
+
 def relu(X):
     torch = _torch()
     n = X.shape[0]

@@ -88,6 +88,8 @@ ZK_HD Fr float_to_fr(float x) {
 
 // relu_kernel decomposition (/root/reference/zkrelu.cu:11-41)
 struct ReluParts { uint32_t q; uint16_t r; bool positive; bool out_of_range; };
+// where zkReLU::operator()'s outputs go when it is applied in the forward product's epilogue (act == nullptr: not applied)
+struct ReluOut { Fr* act; Fr* sign; uint32_t* mag; uint16_t* rem; uint32_t* bad; };
 ZK_HD ReluParts relu_decompose(const Fr& X) {
   Fr x = from_mont(X);
   ReluParts p; p.positive = false; p.out_of_range = false;
@@ -110,6 +112,40 @@ ZK_HD ReluParts relu_decompose(const Fr& X) {
   bool rem_sign = (mag & 32768ull) != 0;
   uint32_t rem_mag = (uint32_t)(mag & 32767ull);
   int32_t rem = rem_sign ? (int32_t)rem_mag - 32768 : (int32_t)rem_mag;
+  p.q = (uint32_t)((mag - (uint64_t)(int64_t)rem) >> 16);
+  p.r = (uint16_t)(rem_mag | (rem_sign ? 0x8000u : 0u));
+  return p;
+}
+
+
+// m * R mod p for a 64-bit integer m (the Montgomery image of a small integer) in TWO CIOS rows instead of eight:
+// mont(a, b) with a two-limb b is a * b * 2^-64, so a = 2^320 mod p gives m * 2^256.  4x fewer wide multiplies than
+// to_mont(); used where an epilogue converts exact integer results (matmul_umma.cu).
+ZK_HD Fr to_mont_u64(uint64_t m) {
+  constexpr int N = 8;
+  const uint32_t a[N] = {0x0121c884u, 0xc98da28eu, 0xc7363c67u, 0xe6f4f4a0u, 0xe92e7df1u, 0xb2d6ebc4u, 0x9d26242au, 0x19ae5794u};   // 2^320 mod p
+  uint32_t ev[N], od[N];
+  mont_row<FrParams, true>(ev, od, a, (uint32_t)m);
+  mont_row<FrParams, false>(od, ev, a, (uint32_t)(m >> 32));
+  Fr r;
+  r.v[0] = add_cc(ev[0], od[1]);
+  _Pragma("unroll") for (int i = 1; i < N - 1; ++i) r.v[i] = addc_cc(ev[i], od[i + 1]);
+  r.v[N - 1] = addc(ev[N - 1], 0u);
+  final_sub(r);
+  return r;
+}
+
+// relu_decompose for an exact integer pre-activation (the forward product's accumulator): same parts as
+// relu_decompose(to_mont(v mod p)) without the field round trip.
+ZK_HD ReluParts relu_decompose_i64(long long v) {
+  ReluParts p;
+  p.positive = v >= 0 && v < (1ll << 47);
+  const bool negative = v < 0 && v >= -(1ll << 47);
+  p.out_of_range = !p.positive && !negative;
+  const uint64_t mag = p.positive ? (uint64_t)v : negative ? (uint64_t)((1ll << 47) + v) : 0ull;
+  const bool rem_sign = (mag & 32768ull) != 0;
+  const uint32_t rem_mag = (uint32_t)(mag & 32767ull);
+  const int32_t rem = rem_sign ? (int32_t)rem_mag - 32768 : (int32_t)rem_mag;
   p.q = (uint32_t)((mag - (uint64_t)(int64_t)rem) >> 16);
   p.r = (uint16_t)(rem_mag | (rem_sign ? 0x8000u : 0u));
   return p;

@@ -25,7 +25,7 @@ struct zkdl_mm_weights {
 
 namespace zk {
 bool umma_matmul_shape_ok(size_t M, size_t K, size_t N);
-int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, size_t K, size_t N, const uint32_t* info, cudaStream_t st);
+int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, size_t K, size_t N, const uint32_t* info, const ReluOut& ro, cudaStream_t st);
 
 static constexpr int THREADS = 256;
 static inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -373,8 +373,26 @@ int wfold_rows(const zkdl_mm_weights* p, size_t window, const zkdl_fr_t* u_host,
   return ZK_OK;
 }
 
-static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr* C, size_t rowsA, size_t colsA, size_t colsB, cudaStream_t st) {
+// zkReLU::operator() (zkrelu.cu:44-52) on a finished product, unless the tcgen05 kernel already applied it in its epilogue
+// (*skip != 0: the device-side route took the tensor-core path)
+__global__ void __launch_bounds__(THREADS) k_relu_after(const Fr* __restrict__ Z, ReluOut ro, size_t n, const uint32_t* __restrict__ skip) {
+  if (skip && *skip) return;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    ReluParts p = relu_decompose(Z[i]);
+    if (p.out_of_range && ro.bad) atomicAdd(ro.bad, 1u);
+    ro.sign[i] = p.positive ? Fr::one() : Fr::zero();
+    Fr q = Fr::zero(); q.v[0] = p.q;
+    ro.act[i] = p.positive ? to_mont(q) : Fr::zero();
+    ro.mag[i] = p.q; ro.rem[i] = p.r;
+  }
+}
+
+static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr* C, size_t rowsA, size_t colsA, size_t colsB, cudaStream_t st,
+                      const ReluOut* relu = nullptr) {
   Scratch ai, wi, info, ap; int rc;
+  const ReluOut none = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool fused = false;
+  if (relu && relu->bad) ZK_CUDA(cudaMemsetAsync(relu->bad, 0, sizeof(uint32_t), st));
   const bool tc_shape = prep && prep->planes && rowsA % TC_M == 0;
   if ((rc = ai.alloc(sizeof(int32_t) * rowsA * colsA, st))) return rc;
   if ((rc = info.alloc(sizeof(uint32_t) * 8, st))) return rc;
@@ -397,7 +415,10 @@ static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr*
     ZK_LAUNCH(k_fr_to_i32<TC_A_PLANES><<<stream_grid(rowsA * colsA, THREADS), THREADS, 0, st>>>(A, ai.as<int32_t>(), rowsA * colsA, inf, inf + 1, ap.as<uint8_t>()));
     ZK_LAUNCH(k_mm_route<<<1, 1, 0, st>>>(inf, 1));
     // tcgen05 / TMEM / TMA kernel (matmul_umma.cu) when the shape tiles by 128 x 64 x 128, else the mma.sync kernel
-    if (!umma_matmul_shape_ok(rowsA, colsA, colsB) || umma_matmul_launch(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf, st) != ZK_OK) {
+    fused = relu && umma_matmul_shape_ok(rowsA, colsA, colsB);
+    if (!umma_matmul_shape_ok(rowsA, colsA, colsB) ||
+        umma_matmul_launch(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf, relu ? *relu : none, st) != ZK_OK) {
+      fused = false;
       dim3 tgrid(div_up(colsB, TC_N), div_up(rowsA, TC_M));
       ZK_LAUNCH(k_tc_matmul<<<tgrid, 256, 0, st>>>(ap.as<uint8_t>(), prep->planes, C, rowsA, colsA, colsB, inf));
     }
@@ -408,6 +429,10 @@ static int matmul_run(const Fr* A, const Fr* W, const zkdl_mm_weights* prep, Fr*
   ZK_LAUNCH(k_i32_matmul<<<igrid, 256, 0, st>>>(ai.as<int32_t>(), w32, C, rowsA, colsA, colsB, inf));
   dim3 grid(div_up(colsB, MM_TILE), div_up(rowsA, MM_TILE));
   ZK_LAUNCH(k_fr_matmul<<<grid, MM_TILE * MM_TILE, 0, st>>>(A, W, C, rowsA, colsA, colsB, inf));
+  if (relu) {
+    const size_t n = rowsA * colsB;
+    ZK_LAUNCH(k_relu_after<<<stream_grid(n, THREADS), THREADS, 0, st>>>(C, *relu, n, fused ? inf + 4 : nullptr));
+  }
   return ZK_OK;
 }
 
@@ -460,6 +485,15 @@ int zkdl_fr_matmul_prepared(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_m
   if (rowsA == 0) return ZK_OK;
   ZK_REQUIRE(A && W && C, ZK_ERR_ARG, "null argument");
   return matmul_run(F(A), F(W), prep, F(C), rowsA, prep->rows, prep->cols, S(stream));
+}
+
+int zkdl_fr_matmul_prepared_relu(const zkdl_fr_t* A, const zkdl_fr_t* W, const zkdl_mm_weights* prep, zkdl_fr_t* Z, size_t rowsA,
+                                 zkdl_fr_t* act, zkdl_fr_t* sign, uint32_t* mag_packed, uint16_t* rem_packed, uint32_t* out_of_range, void* stream) {
+  ZK_REQUIRE(prep, ZK_ERR_ARG, "null argument");
+  if (rowsA == 0) return ZK_OK;
+  ZK_REQUIRE(A && W && Z && act && sign && mag_packed && rem_packed, ZK_ERR_ARG, "null argument");
+  const ReluOut ro = {F(act), F(sign), mag_packed, rem_packed, out_of_range};
+  return matmul_run(F(A), F(W), prep, F(Z), rowsA, prep->rows, prep->cols, S(stream), &ro);
 }
 
 }  // extern "C"

@@ -15,6 +15,9 @@
 //   warps 0-15       epilogue: tcgen05.ld 32x32b (warp w reads TMEM lanes 32 (w % 4) .. +31 = output rows, columns
 //                    16 (w / 4) .. +15), recombination, to_mont, 32-byte stores.  (With 4 warps the epilogue - 64 dependent
 //                    Montgomery products per thread, one warp per scheduler - took 4x longer than the whole main loop.)
+//                    Integers go to Montgomery form with to_mont_u64 (two CIOS rows).  With a ReluOut the epilogue also
+//                    applies zkReLU::operator() to the exact integer: activation, sign and the packed decomposition
+//                    are written from the same registers, so the separate relu pass (re-read Z, from_mont) disappears.
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -30,6 +33,8 @@ constexpr int STAGE_BYTES = NA * A_BYTES + NW * W_BYTES;             // 64 KiB
 constexpr int TMEM_COLS = 256;                                       // 4 accumulators x 64 columns
 constexpr int NTHREADS = 512;                                        // 16 warps: 4 lane quarters x 4 column chunks of 16 in the epilogue
 static_assert(BN == 16 * (NTHREADS / 128), "one 16-column chunk per epilogue warp");
+constexpr int EPI_ROW = 4 * 32 + 16, EPI_BUF = 32 * EPI_ROW;         // epilogue transpose: 32 rows x 4 elements, padded rows
+static_assert((size_t)(NTHREADS / 32) * 2 * EPI_BUF <= (size_t)STAGES * STAGE_BYTES, "the epilogue slices live in the idle stage ring");
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers + TMEM slot */;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,7 +87,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
-                                                        Fr* __restrict__ C, uint32_t M, uint32_t K, uint32_t N, const uint32_t* __restrict__ info) {
+                                                        Fr* __restrict__ C, uint32_t M, uint32_t K, uint32_t N, const uint32_t* __restrict__ info,
+                                                        ReluOut ro) {
   if (!info[4]) return;                                               // routed elsewhere (operands not small enough)
   extern __shared__ uint8_t umma_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(umma_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -158,17 +164,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_consta
 #pragma unroll
     for (int s = 0; s < 4; ++s) tmem_ld16(lane_base + s * BN + c, acc[s]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll 4
-    for (int j = 0; j < 16; ++j) {
-      long long v = 0;
+    // A TMEM lane is an output ROW, so a thread's 32-byte results lie N * 32 bytes apart across the warp: written directly,
+    // every store instruction touches 32 cache lines and the epilogue - not the MMAs - bounds the kernel.  The stage ring is
+    // idle now (every MMA has completed): each warp transposes 4 columns at a time through its own padded slice of it
+    // (row stride 144 B: conflict-free 16-byte accesses both ways) and writes 128-byte row segments, 4 lines per instruction.
+    uint8_t* zb = smem + warp * (2 * EPI_BUF);
+    uint8_t* ab = zb + EPI_BUF;
+    const Fr one = Fr::one();
+    const uint4 one_lo = make_uint4(one.v[0], one.v[1], one.v[2], one.v[3]), one_hi = make_uint4(one.v[4], one.v[5], one.v[6], one.v[7]);
+    const size_t tile_row = (size_t)row0 + quarter * 32;
 #pragma unroll
-      for (int s = 3; s >= 0; --s) v = v * 256 + (long long)(int32_t)acc[s][j];     // |v| < 2^29 * 2^24 * 1.01
-      const bool negative = v < 0;
-      const unsigned long long m = negative ? (unsigned long long)(-v) : (unsigned long long)v;
-      Fr r = Fr::zero();
-      r.v[0] = (uint32_t)m; r.v[1] = (uint32_t)(m >> 32);
-      r = to_mont(r);
-      C[grow * N + col0 + c + j] = negative ? neg(r) : r;
+    for (int q = 0; q < 4; ++q) {
+      uint32_t smask = 0;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = 4 * q + jj;
+        long long v = 0;
+#pragma unroll
+        for (int s = 3; s >= 0; --s) v = v * 256 + (long long)(int32_t)acc[s][j];   // |v| < 2^29 * 2^24 * 1.01
+        const bool negative = v < 0;
+        Fr r = to_mont_u64(negative ? (unsigned long long)(-v) : (unsigned long long)v);
+        if (negative) r = neg(r);
+        uint4* zs = reinterpret_cast<uint4*>(zb + lane * EPI_ROW + jj * 32);
+        zs[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]); zs[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+        if (ro.act) {                                                  // zkReLU::operator() on the exact integer (zkrelu.cu:11-52)
+          const ReluParts p = relu_decompose_i64(v);
+          if (p.out_of_range && ro.bad) atomicAdd(ro.bad, 1u);
+          const Fr a = p.positive ? to_mont_u64(p.q) : Fr::zero();
+          uint4* as = reinterpret_cast<uint4*>(ab + lane * EPI_ROW + jj * 32);
+          as[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); as[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+          smask |= (p.positive ? 1u : 0u) << jj;
+          acc[0][j] = p.q; acc[1][j] = p.r;                           // the accumulators are consumed: reuse them as staging
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int id = it * 32 + lane, row = id >> 3, ch = id & 7;    // 8 x 16 B = one row's 4 elements
+        const size_t g = ((tile_row + row) * N + col0 + c + 4 * q) * sizeof(Fr) + ch * 16;
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(C) + g) = *reinterpret_cast<const uint4*>(zb + row * EPI_ROW + ch * 16);
+        if (ro.act) {
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ro.act) + g) = *reinterpret_cast<const uint4*>(ab + row * EPI_ROW + ch * 16);
+          const uint32_t m = __shfl_sync(0xffffffffu, smask, row);
+          const bool pos = (m >> (ch >> 1)) & 1u;
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ro.sign) + g) = pos ? ((ch & 1) ? one_hi : one_lo) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      __syncwarp();
+    }
+    if (ro.act) {                                                     // 16 consecutive packed values per thread: 64 + 32 aligned bytes
+      const size_t idx = grow * N + col0 + c;
+      uint4* q4 = reinterpret_cast<uint4*>(ro.mag + idx);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) q4[j] = make_uint4(acc[0][4 * j], acc[0][4 * j + 1], acc[0][4 * j + 2], acc[0][4 * j + 3]);
+      uint4* r4 = reinterpret_cast<uint4*>(ro.rem + idx);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        r4[j] = make_uint4(acc[1][8 * j] | (acc[1][8 * j + 1] << 16), acc[1][8 * j + 2] | (acc[1][8 * j + 3] << 16),
+                           acc[1][8 * j + 4] | (acc[1][8 * j + 5] << 16), acc[1][8 * j + 6] | (acc[1][8 * j + 7] << 16));
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -207,7 +260,7 @@ bool umma_matmul_shape_ok(size_t M, size_t K, size_t N) {
 
 // Ap: [3][M][K] byte planes of A, Wp: [2][N][K] byte planes of W^T (same buffers as k_tc_matmul).  Returns -1 if the tensor
 // maps cannot be built (the caller then launches the mma.sync kernel).
-int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, size_t K, size_t N, const uint32_t* info, cudaStream_t st) {
+int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, size_t K, size_t N, const uint32_t* info, const ReluOut& ro, cudaStream_t st) {
   CUtensorMap mapA, mapW;
   if (!umma::make_map(&mapA, Ap, 3 * M, K, umma::BM) || !umma::make_map(&mapW, Wp, 2 * N, K, umma::BN)) return -1;
   static bool attr_set = false;
@@ -216,7 +269,7 @@ int umma_matmul_launch(const uint8_t* Ap, const uint8_t* Wp, Fr* C, size_t M, si
     attr_set = true;
   }
   dim3 grid((unsigned)(N / umma::BN), (unsigned)(M / umma::BM));
-  ZK_LAUNCH(umma::k_umma_matmul<<<grid, umma::NTHREADS, umma::SMEM_BYTES, st>>>(mapA, mapW, C, (uint32_t)M, (uint32_t)K, (uint32_t)N, info));
+  ZK_LAUNCH(umma::k_umma_matmul<<<grid, umma::NTHREADS, umma::SMEM_BYTES, st>>>(mapA, mapW, C, (uint32_t)M, (uint32_t)K, (uint32_t)N, info, ro));
   return ZK_OK;
 }
 

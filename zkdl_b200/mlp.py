@@ -78,12 +78,12 @@ class MLPProver:
         if i == 0:
             X = zk.float_to_fr(cur.contiguous(), self.B, L.I)                                # zkfc.cu:106-115
             self.X = cur = zk.fr_elementwise(zk.OP_MONT, X, out=X)                           # demo.cu:119
+        if i + 1 < len(self.layers):                                                         # product + zkReLU in one call, aux kept bit-packed
+            z, a, sign, mag, rem, bad = zk.fr_matmul_prepared_relu(cur, L.mm, self.B)
+            self.Z.append(z); self.A.append(a); self.aux.append((sign, mag, rem)); self.bad.append(bad)
+            return a
         z = zk.fr_matmul_prepared(cur, L.mm, self.B)
         self.Z.append(z)
-        if i + 1 < len(self.layers):
-            a, sign, mag, rem, bad = zk.relu_packed(z)                                      # aux kept bit-packed
-            self.A.append(a); self.aux.append((sign, mag, rem)); self.bad.append(bad)
-            return a
         return z
 
     def _forward_graph(self, x):
@@ -109,7 +109,7 @@ class MLPProver:
             cur = None
             for i in range(len(self.layers)):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool, stream=st):
+                with torch.cuda.graph(g, pool=pool, stream=st, capture_error_mode="thread_local"):   # NCCL watchdog / pool threads may touch CUDA meanwhile
                     cur = self._forward_layer(i, self._fg_x if i == 0 else cur)
                 self._fg_graphs.append(g)
             self._fg_key = key
