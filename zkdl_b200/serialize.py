@@ -155,7 +155,8 @@ def dumps(public, tasks, fiat_shamir=False, linked=None):
     in proving order; batch is stored in the header.  Version 1 = injected challenges (stored per task); version 2 =
     Fiat-Shamir mode (zkdl_b200/fiat_shamir.py): same layout, every task's challenge list is empty - the verifier derives them.
     Version 3 = linked mode (zkdl_b200/linked.py): version 2 plus, after the public part, the input and output tables and the
-    three auxiliary row commitments (sign, mag_bin, rem_bin) of every zkReLU layer; linked = {"input", "output", "aux_com"}."""
+    three auxiliary row commitments (sign, mag_bin, rem_bin) of every zkReLU layer (uncompressed, like the generators);
+    linked = {"input", "output", "aux_com"}."""
     out = [MAGIC, _u32(3 if linked is not None else 2 if fiat_shamir else 1, len(public["layers"]), public["batch"])]
     for L in public["layers"]:
         out.append(_u32(L["in_dim"], L["out_dim"], L["I"], L["O"], len(L["generators"]), len(L["commitment"])))
@@ -167,7 +168,7 @@ def dumps(public, tasks, fiat_shamir=False, linked=None):
         out.append(_u32(len(linked["aux_com"])))
         for coms in linked["aux_com"]:
             for c in coms:
-                out.append(_u32(len(c))); out.append(g1_compress(c))
+                out.append(_u32(len(c))); out.append(g1_uncompressed(c))    # ~10^5 points for the demo model: no square roots on load
     out.append(_u32(len(tasks)))
     for t in tasks:
         out.append(_u32(0 if t["kind"] == "fc" else 1, t["layer"], len(t["challenges"])))
@@ -212,7 +213,7 @@ def loads(buf):
     linked = None
     if version == 3:
         linked = {"input": fr_from_bytes(r.take(32 * r.u32())), "output": fr_from_bytes(r.take(32 * r.u32()))}
-        linked["aux_com"] = [[g1_decompress(r.take(48 * r.u32())) for _ in range(3)] for _ in range(r.u32())]
+        linked["aux_com"] = [[g1_from_uncompressed(r.take(96 * r.u32())) for _ in range(3)] for _ in range(r.u32())]
     tasks = []
     for _ in range(r.u32()):
         kind, layer, nch = r.u32(3)
