@@ -39,6 +39,7 @@ void hs_bin_pair_c12(const Fr* a0, const Fr* a1, const Fr* e, const Fr* x, Fr* c
   for (size_t i = 0; i < n; ++i) ao[i] = bin_pair_c12(a0[i], a1[i], e[i], *x, c + 3 * i);
 }
 void hs_to_mont_u64(const uint64_t* m, Fr* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = to_mont_u64(m[i]); }
+void hs_to_mont_u32(const uint32_t* m, Fr* o, size_t n) { for (size_t i = 0; i < n; ++i) o[i] = to_mont_u32(m[i]); }
 void hs_relu_i64(const long long* v, uint32_t* q, uint16_t* r, int* pos, int* bad, size_t n) {
   for (size_t i = 0; i < n; ++i) { ReluParts p = relu_decompose_i64(v[i]); q[i] = p.q; r[i] = p.r; pos[i] = p.positive; bad[i] = p.out_of_range; }
 }

@@ -123,6 +123,10 @@ def test_short_to_mont_and_integer_relu(hs):
     o = np.zeros((len(ms), 8), np.uint32)
     hs.hs_to_mont_u64(p(m), p(o), C.c_size_t(len(ms)))
     assert np.array_equal(o, orc.fr_from_ints(ms))
+    m32 = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF] + [int(v) for v in rng.integers(0, 1 << 32, size=300)]
+    o32 = np.zeros((len(m32), 8), np.uint32)
+    hs.hs_to_mont_u32(p(np.array(m32, dtype=np.uint32)), p(o32), C.c_size_t(len(m32)))
+    assert np.array_equal(o32, orc.fr_from_ints(m32))
     xs = [int(v) for v in rng.integers(-(1 << 46), 1 << 46, size=400)] + [0, 1, -1, 32767, 32768, -32768, -32769, 65535, 65536, (1 << 47) - 1, -(1 << 47), 1 << 47,
                                                                            -(1 << 47) - 1, (1 << 53), -(1 << 53)]
     n = len(xs)

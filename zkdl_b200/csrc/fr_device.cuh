@@ -135,6 +135,20 @@ ZK_HD Fr to_mont_u64(uint64_t m) {
   return r;
 }
 
+// the same for a 32-bit integer: ONE row against 2^288 mod p (the rescaled ReLU magnitudes are 32-bit)
+ZK_HD Fr to_mont_u32(uint32_t m) {
+  constexpr int N = 8;
+  const uint32_t a[N] = {0xcaaf6b13u, 0x355094eau, 0x69a568efu, 0xf6b10cb3u, 0x40cc3869u, 0xe2c926a6u, 0xed269aadu, 0x736a6d3bu};   // 2^288 mod p
+  uint32_t ev[N], od[N];
+  mont_row<FrParams, true>(od, ev, a, m);                 // roles as after the last row of an even-length product
+  Fr r;
+  r.v[0] = add_cc(ev[0], od[1]);
+  _Pragma("unroll") for (int i = 1; i < N - 1; ++i) r.v[i] = addc_cc(ev[i], od[i + 1]);
+  r.v[N - 1] = addc(ev[N - 1], 0u);
+  final_sub(r);
+  return r;
+}
+
 // relu_decompose for an exact integer pre-activation (the forward product's accumulator): same parts as
 // relu_decompose(to_mont(v mod p)) without the field round trip.
 ZK_HD ReluParts relu_decompose_i64(long long v) {

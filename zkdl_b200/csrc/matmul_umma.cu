@@ -79,6 +79,16 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_c, uint64_t adesc, uint64_t
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// 16-byte shared-memory accesses by 32-bit shared address: the staging pointer is derived through an integer round-up, so the
+// compiler would otherwise emit generic LD / ST (L1TEX address translation, long-scoreboard latency) instead of LDS / STS
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
@@ -168,8 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_consta
     // every store instruction touches 32 cache lines and the epilogue - not the MMAs - bounds the kernel.  The stage ring is
     // idle now (every MMA has completed): each warp transposes 4 columns at a time through its own padded slice of it
     // (row stride 144 B: conflict-free 16-byte accesses both ways) and writes 128-byte row segments, 4 lines per instruction.
-    uint8_t* zb = smem + warp * (2 * EPI_BUF);
-    uint8_t* ab = zb + EPI_BUF;
+    const uint32_t zb = smem_base + warp * (2 * EPI_BUF), ab = zb + EPI_BUF;
     const Fr one = Fr::one();
     const uint4 one_lo = make_uint4(one.v[0], one.v[1], one.v[2], one.v[3]), one_hi = make_uint4(one.v[4], one.v[5], one.v[6], one.v[7]);
     const size_t tile_row = (size_t)row0 + quarter * 32;
@@ -185,14 +194,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_consta
         const bool negative = v < 0;
         Fr r = to_mont_u64(negative ? (unsigned long long)(-v) : (unsigned long long)v);
         if (negative) r = neg(r);
-        uint4* zs = reinterpret_cast<uint4*>(zb + lane * EPI_ROW + jj * 32);
-        zs[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]); zs[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+        const uint32_t zs = zb + lane * EPI_ROW + jj * 32;
+        sts128(zs, r.v[0], r.v[1], r.v[2], r.v[3]); sts128(zs + 16, r.v[4], r.v[5], r.v[6], r.v[7]);
         if (ro.act) {                                                  // zkReLU::operator() on the exact integer (zkrelu.cu:11-52)
           const ReluParts p = relu_decompose_i64(v);
           if (p.out_of_range && ro.bad) atomicAdd(ro.bad, 1u);
-          const Fr a = p.positive ? to_mont_u64(p.q) : Fr::zero();
-          uint4* as = reinterpret_cast<uint4*>(ab + lane * EPI_ROW + jj * 32);
-          as[0] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]); as[1] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
+          const Fr a = p.positive ? to_mont_u32(p.q) : Fr::zero();
+          const uint32_t as = ab + lane * EPI_ROW + jj * 32;
+          sts128(as, a.v[0], a.v[1], a.v[2], a.v[3]); sts128(as + 16, a.v[4], a.v[5], a.v[6], a.v[7]);
           smask |= (p.positive ? 1u : 0u) << jj;
           acc[0][j] = p.q; acc[1][j] = p.r;                           // the accumulators are consumed: reuse them as staging
         }
@@ -202,9 +211,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_umma_matmul(const __grid_consta
       for (int it = 0; it < 8; ++it) {
         const int id = it * 32 + lane, row = id >> 3, ch = id & 7;    // 8 x 16 B = one row's 4 elements
         const size_t g = ((tile_row + row) * N + col0 + c + 4 * q) * sizeof(Fr) + ch * 16;
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(C) + g) = *reinterpret_cast<const uint4*>(zb + row * EPI_ROW + ch * 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(C) + g) = lds128(zb + row * EPI_ROW + ch * 16);
         if (ro.act) {
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ro.act) + g) = *reinterpret_cast<const uint4*>(ab + row * EPI_ROW + ch * 16);
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ro.act) + g) = lds128(ab + row * EPI_ROW + ch * 16);
           const uint32_t m = __shfl_sync(0xffffffffu, smask, row);
           const bool pos = (m >> (ch >> 1)) & 1u;
           *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ro.sign) + g) = pos ? ((ch & 1) ? one_hi : one_lo) : make_uint4(0, 0, 0, 0);
