@@ -53,6 +53,13 @@ def test_linked_chain_verifies_and_rejects_tampering(cpu_zk, toy, tmp_path):
     tampered(lambda p: bump(p["steps"][3]["bin_sign"], -1))
     tampered(lambda p: bump(p["steps"][3]["opens"][4]["ret"]))             # an opened value
     tampered(lambda p: p["steps"].pop())                                   # a missing link
+    tampered(lambda p: p["aux_com"][0].reverse())                          # sign / rem commitments swapped
+    # the public model is part of the transcript root: another generator or weight commitment changes every challenge
+    for key, row in (("generators", 1), ("commitment", 0)):
+        pub = copy.deepcopy(public)
+        pub[1][key][row] = pub[1][key][row + 1]
+        with pytest.raises(verify.VerifyError):
+            linked.verify_linked(pub, proof)
 
 
 def test_linked_rejects_a_wrong_activation(cpu_zk):
