@@ -113,6 +113,10 @@ class MLPProver:
                     cur = self._forward_layer(i, self._fg_x if i == 0 else cur)
                 self._fg_graphs.append(g)
             self._fg_key = key
+            self._fg_tables = (self.X, list(self.Z), list(self.A), list(self.aux), list(self.bad))
+        # the tables the graphs write (an eager forward() in between rebinds self.Z ... to its own tensors)
+        self.B = pad2(x.shape[0])
+        self.X, self.Z, self.A, self.aux, self.bad = (self._fg_tables[0], *(list(t) for t in self._fg_tables[1:]))
         self._fg_x.copy_(x, non_blocking=True)
         self.ready = []
         for g in self._fg_graphs:
